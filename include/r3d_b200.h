@@ -1,0 +1,176 @@
+/*
+ * r3d_b200.h -- C ABI of the B200-native SH-voxel-grid volumetric renderer.
+ *
+ * This is the drop-in boundary for ONE hot path of akanimax/thr3ed_atom: the render procedure
+ *     thre3d_atom/thre3d_reprs/renderers.py:48-102   render_sh_voxel_grid(voxel_grid, rays, cfg)
+ * (sampler -> point processor -> accumulator, rendering/volumetric/render_interface.py:103-134)
+ * and autograd's backward of it into VoxelGrid._densities / ._features.  The reference has no FFI
+ * (it is pure Python); these entry points are what a ctypes binding inside the reference's
+ * renderers.py would call -- see INTEGRATION.md for that stub.
+ *
+ * Conventions
+ *  - Plain C: raw device pointers + sizes, no torch / C++ types.  All arrays are fp32, contiguous.
+ *  - The caller (PyTorch) allocates and owns every buffer, including outputs and gradient buffers.
+ *    Gradient buffers are ACCUMULATED into (caller zeroes them), so several ray batches / several
+ *    renders can share one buffer exactly like autograd's .grad accumulation.
+ *  - Work is enqueued on the given CUDA stream (cudaStream_t passed as void*); no internal
+ *    synchronisation, no global mutable state apart from the thread-local error string.
+ *  - Every function returns R3D_OK (0) or an error code; r3d_last_error() gives the message.
+ *    No C++ exception crosses this boundary.
+ */
+#ifndef R3D_B200_H_
+#define R3D_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define R3D_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define R3D_API __attribute__((visibility("default")))
+#else
+#define R3D_API
+#endif
+
+enum R3dStatus {
+  R3D_OK = 0,
+  R3D_ERR_INVALID_ARGUMENT = 1,
+  R3D_ERR_UNSUPPORTED = 2,
+  R3D_ERR_CUDA = 3
+};
+
+/* density activations selectable by the reference's train script
+ * (thre3d_elements/relu_fields/train_sh_based_voxel_grid_with_posed_images.py:169-192) */
+enum R3dDensityPre { R3D_PRE_IDENTITY = 0, R3D_PRE_ABS = 1 };
+enum R3dDensityPost { R3D_POST_IDENTITY = 0, R3D_POST_RELU = 1, R3D_POST_SOFTPLUS = 2 };
+
+/* SHVoxGridRenderConfig booleans (thre3d_reprs/renderers.py:28-45) */
+enum R3dRenderFlags {
+  R3D_FLAG_PERTURB = 1u << 0,            /* perturb_sampled_points */
+  R3D_FLAG_WHITE_BKGD = 1u << 1,         /* white_bkgd */
+  R3D_FLAG_DIFFUSE = 1u << 2,            /* render_diffuse: SH band 0 only (process.py:59-63) */
+  R3D_FLAG_OPTIMIZED_SAMPLING = 1u << 3  /* optimized_sampling: per-ray near/far from the slab test (sample.py:71-202) */
+};
+
+/* A dense voxel grid = reference VoxelGrid (thre3d_reprs/voxels.py:46-124).
+ * Index order V[ix][iy][iz][channel], channel fastest -- the reference's own layout (voxels.py:70-71).
+ * `features` may be padded: `feature_stride` floats per voxel record, of which the first
+ * `num_features` = 3*(sh_degree+1)^2 are used (channel-major: coeff[ch][k] = rec[ch*K + k],
+ * process.py:61,66).  A stride that is a multiple of 4 with a 16-byte aligned base enables 128-bit
+ * vector loads / reductions; the unpadded reference layout (stride == num_features) also works. */
+typedef struct R3dGrid {
+  const float* densities;  /* [W][D][H]          raw (pre-activation, un-scaled) density */
+  const float* features;   /* [W][D][H][feature_stride] */
+  int32_t dims[3];         /* W (x), D (y), H (z)  voxels.py:116-121 */
+  int32_t sh_degree;       /* 0..3 (spherical_harmonics.py:79) */
+  int32_t num_features;    /* 3*(sh_degree+1)^2 */
+  int32_t feature_stride;  /* >= num_features */
+  float aabb_min[3];       /* voxels.py:187-212, rounded to fp32 (what the fp32 comparisons at :262-272 see) */
+  float aabb_max[3];
+  float norm_scale[3];     /* n = p*scale + bias maps the AABB to [-1,1]; fp32 values of */
+  float norm_bias[3];      /*   utils/imaging_utils.py:58-63 (adjust_dynamic_range, slack=True) */
+  float density_scale;     /* expected_density_scale (voxels.py:63,292-294) */
+  int32_t density_pre;     /* R3dDensityPre  */
+  int32_t density_post;    /* R3dDensityPost */
+} R3dGrid;
+
+/* Pinhole camera for in-kernel ray generation = cast_rays (rendering/volumetric/utils/misc.py:12-50). */
+typedef struct R3dCamera {
+  int32_t height, width;
+  float focal;
+  float rotation[9];     /* row-major 3x3 camera-to-world */
+  float translation[3];
+} R3dCamera;
+
+/* A flat batch of rays = reference Rays (render_interface.py:14-44), always [N,3] (:127-129). */
+typedef struct R3dRays {
+  const float* origins;     /* [N][3]; may be NULL when `camera` is given (rays are generated in-kernel) */
+  const float* directions;  /* [N][3]; need not be unit length */
+  const float* bounds;      /* optional [N][2] per-ray (near, far) (sample.py:42-43); NULL = cfg near/far */
+  const R3dCamera* camera;  /* optional HOST pointer; N must equal height*width, ray r = y*width + x */
+  int64_t num_rays;
+  int32_t tile_width;       /* optional coherence hint: rays are a row-major image of this width (0 = unknown). */
+  int32_t tile_height;      /*   Threads are then mapped to 8x4 pixel tiles; results are identical either way. */
+} R3dRays;
+
+typedef struct R3dRenderConfig {
+  int32_t num_samples;   /* num_samples_per_ray */
+  float near, far;       /* camera_bounds */
+  uint32_t flags;        /* R3dRenderFlags */
+  const float* jitter;   /* optional [N][S] U[0,1) stratified offsets (what the reference draws with torch.rand,
+                            sample.py:63).  NULL with R3D_FLAG_PERTURB => counter-based in-kernel RNG below. */
+  uint64_t rng_seed;     /* in-kernel jitter = hash(seed, ray, sample); the backward pass re-derives it */
+  int32_t variant;       /* kernel variant selector for A/B measurement; 0 = default */
+} R3dRenderConfig;
+
+/* = reference RenderOut (render_interface.py:47-83) with extra{disparity, accumulated_weight}. */
+typedef struct R3dRenderOut {
+  float* colour;     /* [N][3] */
+  float* depth;      /* [N]    (== [N][1]) */
+  float* acc;        /* [N]    accumulated_weight */
+  float* disparity;  /* [N]    may be NULL */
+} R3dRenderOut;
+
+/* upstream gradients dL/d(output); any pointer may be NULL (= zero). */
+typedef struct R3dRenderOutGrad {
+  const float* colour;     /* [N][3] */
+  const float* depth;      /* [N] */
+  const float* acc;        /* [N] */
+  const float* disparity;  /* [N] */
+} R3dRenderOutGrad;
+
+/* gradient buffers, same layout as R3dGrid.densities / .features; accumulated into. */
+typedef struct R3dGridGrad {
+  float* densities;  /* [W][D][H]; may be NULL */
+  float* features;   /* [W][D][H][feature_stride]; may be NULL */
+} R3dGridGrad;
+
+R3D_API int r3d_abi_version(void);
+R3D_API const char* r3d_last_error(void);
+
+/* Forward: replaces render_sh_voxel_grid (thre3d_reprs/renderers.py:48-102) =
+ *   sample_uniform_points_on_rays / sample_aabb_bound_uniform_points_on_rays (sample.py:15-202)
+ *   -> process_points_with_sh_voxel_grid (process.py:20-96) incl. VoxelGrid.forward (voxels.py:276-331),
+ *      test_inside_volume (voxels.py:252-274), evaluate_spherical_harmonics (spherical_harmonics.py:64-116)
+ *   -> accumulate_radiance_density_on_rays (accumulate.py:31-113)
+ * in one fused kernel.  density2occupancy is density2occupancy_pb (accumulate.py:24-28), the tone map is
+ * torch.sigmoid, stochastic_density_noise_std is 0 (the defaults of renderers.py:37-39). */
+R3D_API int r3d_render_fwd(const R3dGrid* grid, const R3dRays* rays, const R3dRenderConfig* cfg,
+                   const R3dRenderOut* out, void* cuda_stream);
+
+/* Backward: replaces autograd's backward of the above into _densities/_features
+ * (the graph behind trainers.py:339-341).  `saved` holds the forward outputs of the same call. */
+R3D_API int r3d_render_bwd(const R3dGrid* grid, const R3dRays* rays, const R3dRenderConfig* cfg,
+                   const R3dRenderOut* saved, const R3dRenderOutGrad* grad_out,
+                   const R3dGridGrad* grad_grid, void* cuda_stream);
+
+/* cast_rays (rendering/volumetric/utils/misc.py:12-50): fills origins/directions [H*W][3]. */
+R3D_API int r3d_cast_rays(const R3dCamera* camera, float* origins, float* directions, void* cuda_stream);
+
+/* VoxelGrid.forward (voxels.py:276-331) on free points: out [P][F+1] = (features..., density);
+ * `inside` (optional, [P] bytes) = test_inside_volume (voxels.py:252-274). */
+R3D_API int r3d_grid_lookup_fwd(const R3dGrid* grid, const float* points, int64_t num_points, float* out,
+                        uint8_t* inside, void* cuda_stream);
+R3D_API int r3d_grid_lookup_bwd(const R3dGrid* grid, const float* points, int64_t num_points,
+                        const float* grad_out, const R3dGridGrad* grad_grid, void* cuda_stream);
+
+/* Measurement helper (not on the product path): marks every voxel that the batch's in-volume
+ * samples reference as an interpolation corner in `bitmap` ([W*D*H] bytes, caller-zeroed), so the
+ * host can count U = unique voxels touched for the algorithmic-bytes figure. */
+R3D_API int r3d_mark_touched_voxels(const R3dGrid* grid, const R3dRays* rays, const R3dRenderConfig* cfg,
+                            uint8_t* bitmap, void* cuda_stream);
+
+/* Fused dense Adam on a grid tensor (next-row f1; replaces torch.optim.Adam at trainers.py:242-245,341).
+ * p, g, m, v: [n] fp32.  Standard Adam (no weight decay, no amsgrad): bias corrections are passed in
+ * as 1-beta^t so the kernel stays stateless. */
+R3D_API int r3d_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                  float lr, float beta1, float beta2, float eps, float bias_correction1,
+                  float bias_correction2, float grad_scale, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* R3D_B200_H_ */

@@ -1,0 +1,256 @@
+"""Tensor-level wrappers of the C ABI (``include/r3d_b200.h``).
+
+PyTorch is plumbing here: it owns device memory and the CUDA stream; every function below packs
+raw ``data_ptr()`` values into the ABI structs and enqueues the library's kernels on
+``torch.cuda.current_stream()``.  Inputs must be fp32 CUDA tensors -- there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+from torch import Tensor
+
+from thr3ed_atom_b200 import _abi
+
+
+def _require_cuda(t: Tensor, name: str) -> Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"{name} is on {t.device}: the B200 render path only runs on CUDA tensors "
+            "(there is deliberately no CPU fallback)."
+        )
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+    return t
+
+
+def _ptr(t: Optional[Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream(device: torch.device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+@dataclasses.dataclass
+class GridDesc:
+    """Everything the kernels need to know about a voxel grid (mirrors ``R3dGrid``)."""
+
+    densities: Tensor  # [W, D, H, 1] contiguous
+    features: Tensor  # [W, D, H, stride] contiguous (first num_features channels used)
+    num_features: int
+    aabb: Tuple[Tuple[float, float], Tuple[float, float], Tuple[float, float]]
+    norm_scale: Sequence[float]
+    norm_bias: Sequence[float]
+    density_scale: float
+    density_pre: int
+    density_post: int
+
+    def to_struct(self) -> _abi.R3dGrid:
+        d = _require_cuda(self.densities, "voxel_grid.densities")
+        f = _require_cuda(self.features, "voxel_grid.features")
+        if not (d.is_contiguous() and f.is_contiguous()):
+            raise RuntimeError("voxel grid storage must be contiguous")
+        if d.device != f.device:
+            raise RuntimeError("densities and features are not on the same device :(")
+        k = self.num_features // 3
+        deg = int(round(k**0.5)) - 1
+        if 3 * (deg + 1) ** 2 != self.num_features:
+            raise ValueError(f"number of features ({self.num_features}) is not 3 * (sh_degree + 1) ** 2")
+        g = _abi.R3dGrid()
+        g.densities, g.features = d.data_ptr(), f.data_ptr()
+        g.dims[:] = list(f.shape[:3])
+        g.sh_degree, g.num_features, g.feature_stride = deg, self.num_features, f.shape[3]
+        g.aabb_min[:] = [float(np.float32(r[0])) for r in self.aabb]
+        g.aabb_max[:] = [float(np.float32(r[1])) for r in self.aabb]
+        g.norm_scale[:] = [float(s) for s in self.norm_scale]
+        g.norm_bias[:] = [float(b) for b in self.norm_bias]
+        g.density_scale = float(self.density_scale)
+        g.density_pre, g.density_post = self.density_pre, self.density_post
+        return g
+
+
+@dataclasses.dataclass
+class RenderArgs:
+    """Per-call render parameters (mirrors ``R3dRenderConfig`` + the ray hints of ``R3dRays``)."""
+
+    num_samples: int
+    near: float
+    far: float
+    perturb: bool = False
+    white_bkgd: bool = False
+    diffuse: bool = False
+    optimized_sampling: bool = False
+    jitter: Optional[Tensor] = None  # explicit [N, S] U[0,1) offsets
+    rng_seed: int = 0
+    ray_bounds: Optional[Tensor] = None  # [N, 2]
+    image_hw: Optional[Tuple[int, int]] = None  # rays are a row-major H x W image (coherence hint)
+    camera: Optional[Tuple[int, int, float, Sequence[float], Sequence[float]]] = None  # (H, W, focal, R9, t3)
+    variant: int = 0
+
+    def flags(self) -> int:
+        return (
+            (_abi.FLAG_PERTURB if self.perturb else 0)
+            | (_abi.FLAG_WHITE_BKGD if self.white_bkgd else 0)
+            | (_abi.FLAG_DIFFUSE if self.diffuse else 0)
+            | (_abi.FLAG_OPTIMIZED_SAMPLING if self.optimized_sampling else 0)
+        )
+
+
+def _pack_call(grid: GridDesc, origins: Optional[Tensor], directions: Optional[Tensor], num_rays: int, args: RenderArgs):
+    g = grid.to_struct()
+    keep = []  # keeps ctypes objects alive until the call returns
+    r = _abi.R3dRays()
+    r.num_rays = num_rays
+    if args.camera is not None:
+        h, w, focal, rot, trans = args.camera
+        cam = _abi.R3dCamera()
+        cam.height, cam.width, cam.focal = int(h), int(w), float(focal)
+        cam.rotation[:] = [float(x) for x in rot]
+        cam.translation[:] = [float(x) for x in trans]
+        keep.append(cam)
+        r.camera = C.pointer(cam)
+    else:
+        o = _require_cuda(origins, "rays.origins")
+        d = _require_cuda(directions, "rays.directions")
+        if not (o.is_contiguous() and d.is_contiguous()):
+            raise RuntimeError("rays must be contiguous [N, 3] tensors")
+        if o.device != grid.features.device:
+            raise RuntimeError(f"rays are on {o.device} but the voxel grid is on {grid.features.device}")
+        r.origins, r.directions = o.data_ptr(), d.data_ptr()
+        if args.image_hw is not None:
+            r.tile_height, r.tile_width = int(args.image_hw[0]), int(args.image_hw[1])
+    if args.ray_bounds is not None:
+        b = _require_cuda(args.ray_bounds, "ray_bounds")
+        if tuple(b.shape) != (num_rays, 2) or not b.is_contiguous():
+            raise ValueError("ray_bounds must be a contiguous [N, 2] tensor")
+        r.bounds = b.data_ptr()
+    c = _abi.R3dRenderConfig()
+    c.num_samples, c.near, c.far = int(args.num_samples), float(args.near), float(args.far)
+    c.flags = args.flags()
+    if args.jitter is not None and args.perturb:
+        j = _require_cuda(args.jitter, "jitter")
+        if tuple(j.shape) != (num_rays, args.num_samples) or not j.is_contiguous():
+            raise ValueError(f"jitter must be a contiguous [{num_rays}, {args.num_samples}] tensor")
+        c.jitter = j.data_ptr()
+    c.rng_seed = int(args.rng_seed) & 0xFFFFFFFFFFFFFFFF
+    c.variant = int(args.variant)
+    return g, r, c, keep
+
+
+def render_forward(grid: GridDesc, origins: Optional[Tensor], directions: Optional[Tensor], args: RenderArgs):
+    """Fused forward render.  Returns ``(colour [N,3], depth [N,1], acc [N,1], disparity [N,1])``."""
+    device = grid.features.device
+    n = origins.shape[0] if args.camera is None else int(args.camera[0]) * int(args.camera[1])
+    colour = torch.empty((n, 3), dtype=torch.float32, device=device)
+    depth = torch.empty((n, 1), dtype=torch.float32, device=device)
+    acc = torch.empty((n, 1), dtype=torch.float32, device=device)
+    disparity = torch.empty((n, 1), dtype=torch.float32, device=device)
+    g, r, c, keep = _pack_call(grid, origins, directions, n, args)
+    out = _abi.R3dRenderOut(colour.data_ptr(), depth.data_ptr(), acc.data_ptr(), disparity.data_ptr())
+    with torch.cuda.device(device):
+        _abi.check(_abi.lib().r3d_render_fwd(C.byref(g), C.byref(r), C.byref(c), C.byref(out), _stream(device)), "r3d_render_fwd")
+    del keep
+    return colour, depth, acc, disparity
+
+
+def render_backward(
+    grid: GridDesc,
+    origins: Optional[Tensor],
+    directions: Optional[Tensor],
+    args: RenderArgs,
+    saved: Tuple[Tensor, Tensor, Tensor],
+    grads: Tuple[Optional[Tensor], Optional[Tensor], Optional[Tensor], Optional[Tensor]],
+    grad_densities: Optional[Tensor],
+    grad_features: Optional[Tensor],
+) -> None:
+    """Fused backward: accumulates into ``grad_densities`` / ``grad_features`` (same layout as the grid)."""
+    device = grid.features.device
+    colour, depth, acc = saved
+    n = colour.shape[0]
+    g, r, c, keep = _pack_call(grid, origins, directions, n, args)
+    sv = _abi.R3dRenderOut(colour.data_ptr(), depth.data_ptr(), acc.data_ptr(), None)
+    gs = [None if t is None else _require_cuda(t.contiguous(), "grad_output") for t in grads]
+    go = _abi.R3dRenderOutGrad(*[_ptr(t) for t in gs])
+    for t, ref in ((grad_densities, grid.densities), (grad_features, grid.features)):
+        if t is not None and (tuple(t.shape) != tuple(ref.shape) or not t.is_contiguous() or t.dtype != torch.float32):
+            raise ValueError("gradient buffers must match the grid storage layout")
+    gg = _abi.R3dGridGrad(_ptr(grad_densities), _ptr(grad_features))
+    with torch.cuda.device(device):
+        _abi.check(
+            _abi.lib().r3d_render_bwd(C.byref(g), C.byref(r), C.byref(c), C.byref(sv), C.byref(go), C.byref(gg), _stream(device)),
+            "r3d_render_bwd",
+        )
+    del keep, gs
+
+
+def mark_touched_voxels(grid: GridDesc, origins: Optional[Tensor], directions: Optional[Tensor], args: RenderArgs) -> Tensor:
+    """uint8 ``[W, D, H]`` bitmap of voxels referenced by in-volume samples (measurement helper)."""
+    device = grid.features.device
+    n = origins.shape[0] if args.camera is None else int(args.camera[0]) * int(args.camera[1])
+    bitmap = torch.zeros(tuple(grid.features.shape[:3]), dtype=torch.uint8, device=device)
+    g, r, c, keep = _pack_call(grid, origins, directions, n, args)
+    with torch.cuda.device(device):
+        _abi.check(_abi.lib().r3d_mark_touched_voxels(C.byref(g), C.byref(r), C.byref(c), bitmap.data_ptr(), _stream(device)), "r3d_mark_touched_voxels")
+    del keep
+    return bitmap
+
+
+def cast_rays(height: int, width: int, focal: float, rotation, translation, device) -> Tuple[Tensor, Tensor]:
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError(f"cast_rays runs on CUDA only (requested {device})")
+    rot = torch.as_tensor(rotation).detach().to("cpu", torch.float32).reshape(9).tolist()
+    trans = torch.as_tensor(translation).detach().to("cpu", torch.float32).reshape(3).tolist()
+    cam = _abi.R3dCamera()
+    cam.height, cam.width, cam.focal = height, width, focal
+    cam.rotation[:] = rot
+    cam.translation[:] = trans
+    origins = torch.empty((height * width, 3), dtype=torch.float32, device=device)
+    directions = torch.empty((height * width, 3), dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        _abi.check(_abi.lib().r3d_cast_rays(C.byref(cam), origins.data_ptr(), directions.data_ptr(), _stream(device)), "r3d_cast_rays")
+    return origins, directions
+
+
+def grid_lookup_forward(grid: GridDesc, points: Tensor, want_inside: bool = False):
+    device = grid.features.device
+    p = _require_cuda(points, "points").contiguous()
+    n = p.shape[0]
+    out = torch.empty((n, grid.num_features + 1), dtype=torch.float32, device=device)
+    inside = torch.empty((n,), dtype=torch.uint8, device=device) if want_inside else None
+    g = grid.to_struct()
+    with torch.cuda.device(device):
+        _abi.check(_abi.lib().r3d_grid_lookup_fwd(C.byref(g), p.data_ptr(), n, out.data_ptr(), _ptr(inside), _stream(device)), "r3d_grid_lookup_fwd")
+    return out, inside
+
+
+def grid_lookup_backward(grid: GridDesc, points: Tensor, grad_out: Tensor, grad_densities: Optional[Tensor], grad_features: Optional[Tensor]) -> None:
+    device = grid.features.device
+    p = _require_cuda(points, "points").contiguous()
+    go = _require_cuda(grad_out, "grad_out").contiguous()
+    g = grid.to_struct()
+    gg = _abi.R3dGridGrad(_ptr(grad_densities), _ptr(grad_features))
+    with torch.cuda.device(device):
+        _abi.check(_abi.lib().r3d_grid_lookup_bwd(C.byref(g), p.data_ptr(), p.shape[0], go.data_ptr(), C.byref(gg), _stream(device)), "r3d_grid_lookup_bwd")
+
+
+def adam_step(param: Tensor, grad: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, *, lr: float, beta1: float, beta2: float,
+              eps: float, step: int, grad_scale: float = 1.0) -> None:
+    for name, t in (("param", param), ("grad", grad), ("exp_avg", exp_avg), ("exp_avg_sq", exp_avg_sq)):
+        _require_cuda(t, name)
+        if not t.is_contiguous() or t.numel() != param.numel():
+            raise ValueError(f"{name} must be contiguous and match param")
+    device = param.device
+    with torch.cuda.device(device):
+        _abi.check(
+            _abi.lib().r3d_adam_step(
+                param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), param.numel(),
+                lr, beta1, beta2, eps, 1.0 - beta1**step, 1.0 - beta2**step, grad_scale, _stream(device),
+            ),
+            "r3d_adam_step",
+        )

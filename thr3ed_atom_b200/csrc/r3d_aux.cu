@@ -1,0 +1,185 @@
+// r3d_aux.cu -- the small kernels around the fused renderer:
+//   r3d_cast_rays          cast_rays                      rendering/volumetric/utils/misc.py:12-50
+//   r3d_grid_lookup_fwd    VoxelGrid.forward + test_inside_volume   thre3d_reprs/voxels.py:252-331
+//   r3d_grid_lookup_bwd    autograd of the lookup into _densities/_features
+//   r3d_adam_step          torch.optim.Adam on the dense grid       modules/trainers.py:242-245,341
+#include "r3d_host.h"
+
+namespace r3d {
+
+__global__ void __launch_bounds__(256) cast_rays_kernel(const R3dCamera cam, float* __restrict__ origins, float* __restrict__ directions) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n = (long long)cam.height * cam.width;
+  if (i >= n) return;
+  Ray r;
+  camera_ray(cam, (int)(i % cam.width), (int)(i / cam.width), r);
+  origins[3 * i] = r.ox, origins[3 * i + 1] = r.oy, origins[3 * i + 2] = r.oz;
+  directions[3 * i] = r.dx, directions[3 * i + 1] = r.dy, directions[3 * i + 2] = r.dz;
+}
+
+// One warp per point, lanes over the channels of a voxel record: every corner record is read with
+// one coalesced request (F contiguous floats), which is the natural mapping for scattered points
+// that share no cells.
+__global__ void __launch_bounds__(256) lookup_fwd_kernel(const GridP g, const float* __restrict__ points, long long n,
+                                                         float* __restrict__ out, uint8_t* __restrict__ inside) {
+  const long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (p >= n) return;
+  const float px = __ldg(points + 3 * p), py = __ldg(points + 3 * p + 1), pz = __ldg(points + 3 * p + 2);
+  Cell c;
+  make_cell(g, px, py, pz, c);
+  if (lane == 0) {
+    float dpost;
+    out[p * (g.F + 1) + g.F] = density_post(g.post, density_pre_interp(g, c), dpost);
+    if (inside) inside[p] = inside_aabb(g, px, py, pz) ? 1 : 0;
+  }
+  for (int e = lane; e < g.F; e += 32) {
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int ix = k >> 2, iy = (k >> 1) & 1, iz = k & 1;
+      const float w = c.wx[ix] * c.wy[iy] * c.wz[iz];
+      const size_t vox = (size_t)(c.ox[ix] + c.oy[iy] + c.oz[iz]);
+      acc = fmaf(w, __ldg(g.feat + vox * (size_t)g.stride + e), acc);
+    }
+    out[p * (g.F + 1) + e] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(256) lookup_bwd_kernel(const GridP g, const float* __restrict__ points, long long n,
+                                                         const float* __restrict__ gout, float* __restrict__ gdens,
+                                                         float* __restrict__ gfeat) {
+  const long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (p >= n) return;
+  const float px = __ldg(points + 3 * p), py = __ldg(points + 3 * p + 1), pz = __ldg(points + 3 * p + 2);
+  Cell c;
+  make_cell(g, px, py, pz, c);
+  if (lane == 0 && gdens) {
+    float dpost;
+    density_post(g.post, density_pre_interp(g, c), dpost);
+    const float dpre = __ldg(gout + p * (g.F + 1) + g.F) * dpost * (g.pre == R3D_PRE_ABS ? fabsf(g.dscale) : g.dscale);
+    if (dpre != 0.f) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int ix = k >> 2, iy = (k >> 1) & 1, iz = k & 1;
+        const float w = c.wx[ix] * c.wy[iy] * c.wz[iz];
+        if (w == 0.f) continue;
+        const size_t vox = (size_t)(c.ox[ix] + c.oy[iy] + c.oz[iz]);
+        float gv = w * dpre;
+        if (g.pre == R3D_PRE_ABS) {
+          const float v = __ldg(g.dens + vox);
+          gv = (v > 0.f) ? gv : ((v < 0.f) ? -gv : 0.f);
+        }
+        atomicAdd(gdens + vox, gv);
+      }
+    }
+  }
+  if (!gfeat) return;
+  for (int e = lane; e < g.F; e += 32) {
+    const float go = __ldg(gout + p * (g.F + 1) + e);
+    if (go == 0.f) continue;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int ix = k >> 2, iy = (k >> 1) & 1, iz = k & 1;
+      const float w = c.wx[ix] * c.wy[iy] * c.wz[iz];
+      if (w == 0.f) continue;
+      const size_t vox = (size_t)(c.ox[ix] + c.oy[iy] + c.oz[iz]);
+      atomicAdd(gfeat + vox * (size_t)g.stride + e, w * go);
+    }
+  }
+}
+
+// Adam, torch.optim.Adam semantics (no weight decay / amsgrad / maximize):
+//   m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
+// Pure streaming kernel: 4 reads + 3 writes of 4 B per element.
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ gr, float* __restrict__ m,
+                                                   float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
+                                                   float bc1, float bc2_sqrt, float gscale) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long n4 = n >> 2;
+  const float step = lr / bc1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 P = reinterpret_cast<float4*>(p)[i];
+    const float4 G = __ldg(reinterpret_cast<const float4*>(gr) + i);
+    float4 M = reinterpret_cast<float4*>(m)[i], V = reinterpret_cast<float4*>(v)[i];
+#define R3D_ADAM1(c)                                         \
+  {                                                          \
+    const float gg = G.c * gscale;                           \
+    M.c = fmaf(b1, M.c, (1.0f - b1) * gg);                   \
+    V.c = fmaf(b2, V.c, (1.0f - b2) * gg * gg);              \
+    P.c -= step * (M.c / (sqrtf(V.c) / bc2_sqrt + eps));     \
+  }
+    R3D_ADAM1(x) R3D_ADAM1(y) R3D_ADAM1(z) R3D_ADAM1(w)
+    reinterpret_cast<float4*>(p)[i] = P;
+    reinterpret_cast<float4*>(m)[i] = M;
+    reinterpret_cast<float4*>(v)[i] = V;
+  }
+  // tail (n % 4 elements)
+  for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float gg = gr[i] * gscale;
+    const float mm = fmaf(b1, m[i], (1.0f - b1) * gg);
+    const float vv = fmaf(b2, v[i], (1.0f - b2) * gg * gg);
+    m[i] = mm, v[i] = vv;
+    p[i] -= step * (mm / (sqrtf(vv) / bc2_sqrt + eps));
+  }
+#undef R3D_ADAM1
+}
+
+}  // namespace r3d
+
+using namespace r3d;
+
+extern "C" int r3d_cast_rays(const R3dCamera* camera, float* origins, float* directions, void* cuda_stream) {
+  if (!camera || !origins || !directions) return fail(R3D_ERR_INVALID_ARGUMENT, "r3d_cast_rays: NULL argument");
+  if (camera->height < 1 || camera->width < 1 || !(camera->focal > 0.f))
+    return fail(R3D_ERR_INVALID_ARGUMENT, "r3d_cast_rays: bad camera intrinsics");
+  const long long n = (long long)camera->height * camera->width;
+  cast_rays_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(*camera, origins, directions);
+  return check_launch("r3d_cast_rays");
+}
+
+extern "C" int r3d_grid_lookup_fwd(const R3dGrid* grid, const float* points, int64_t num_points, float* out, uint8_t* inside,
+                                   void* cuda_stream) {
+  GridP g;
+  int rc;
+  if ((rc = to_device_params(grid, g))) return rc;
+  if (num_points < 0 || (num_points > 0 && (!points || !out))) return fail(R3D_ERR_INVALID_ARGUMENT, "r3d_grid_lookup_fwd: NULL argument");
+  if (num_points == 0) return R3D_OK;
+  const long long blocks = (num_points * 32 + 255) / 256;
+  lookup_fwd_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(g, points, num_points, out, inside);
+  return check_launch("r3d_grid_lookup_fwd");
+}
+
+extern "C" int r3d_grid_lookup_bwd(const R3dGrid* grid, const float* points, int64_t num_points, const float* grad_out,
+                                   const R3dGridGrad* grad_grid, void* cuda_stream) {
+  GridP g;
+  int rc;
+  if ((rc = to_device_params(grid, g))) return rc;
+  if (num_points < 0 || !grad_grid || (num_points > 0 && (!points || !grad_out)))
+    return fail(R3D_ERR_INVALID_ARGUMENT, "r3d_grid_lookup_bwd: NULL argument");
+  if (num_points == 0) return R3D_OK;
+  const long long blocks = (num_points * 32 + 255) / 256;
+  lookup_bwd_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(g, points, num_points, grad_out,
+                                                                                         grad_grid->densities, grad_grid->features);
+  return check_launch("r3d_grid_lookup_bwd");
+}
+
+extern "C" int r3d_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                             float beta2, float eps, float bias_correction1, float bias_correction2, float grad_scale,
+                             void* cuda_stream) {
+  if (n < 0 || (n > 0 && (!param || !grad || !exp_avg || !exp_avg_sq))) return fail(R3D_ERR_INVALID_ARGUMENT, "r3d_adam_step: NULL argument");
+  if (n == 0) return R3D_OK;
+  if (!aligned16(param) || !aligned16(grad) || !aligned16(exp_avg) || !aligned16(exp_avg_sq))
+    return fail(R3D_ERR_INVALID_ARGUMENT, "r3d_adam_step: buffers must be 16-byte aligned");
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  long long blocks = (n / 4 + 255) / 256;
+  const long long cap = (long long)sms * 8;  // persistent grid-stride: a multiple of the SM count
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  adam_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+      param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, bias_correction1, sqrtf(bias_correction2), grad_scale);
+  return check_launch("r3d_adam_step");
+}

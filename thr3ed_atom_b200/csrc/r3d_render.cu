@@ -1,0 +1,464 @@
+// r3d_render.cu -- fused per-ray forward and backward kernels of the SH-voxel-grid renderer (sm_100a).
+//
+// One thread owns one ray and marches it front to back.  Per sample it
+//   1. forms the sample position exactly as the reference does (sample.py:54-67),
+//   2. applies the strict inside-AABB test (voxels.py:252-274 / process.py:80-84),
+//   3. gathers the 8 corner densities (a [W][D][H] fp32 volume: 4 B/voxel, L2 resident up to 256^3+),
+//      interpolates, scales and activates them (voxels.py:292-309),
+//   4. ONLY IF the sample's density is non-zero gathers the 8 corner SH records with 128-bit loads,
+//      contracts each with the ray's SH basis (the contraction is linear, so it commutes with the
+//      trilinear weights: 3 accumulators instead of 3*(deg+1)^2), applies sigmoid and composites
+//      (spherical_harmonics.py:86-116, accumulate.py:43-88).
+// A sample with sigma == 0 has alpha == 0 exactly, hence weight 0 and no effect on colour, depth,
+// acc or the transmittance, and (ReLU' = 0) no gradient: skipping its feature traffic is exact.
+// Likewise a ray whose transmittance reached exactly 0 can stop.
+//
+// The backward kernel re-marches the ray (no per-sample tensors are saved), rebuilding alpha/T/raw,
+// and uses the forward's outputs for the suffix sums:
+//   dL/dsigma_i = delta_i * ( T_{i+1} q_i - sum_{j>i} w_j q_j ),   sum_{j>i} = Total - prefix_i
+//   q_i = g_c . sigmoid(raw_i) + g_d z_i + g_a,  Total = g_c . C_fg + g_d depth + g_a acc
+// (SURVEY.md A.6).  Gradients are scattered with 128-bit vector reductions (red.global.add.v4.f32).
+#include "r3d_host.h"
+
+namespace r3d {
+
+struct OutP {
+  float* __restrict__ colour;
+  float* __restrict__ depth;
+  float* __restrict__ acc;
+  float* __restrict__ disparity;
+};
+
+struct BwdP {
+  const float* __restrict__ colour;  // saved forward outputs
+  const float* __restrict__ depth;
+  const float* __restrict__ acc;
+  const float* __restrict__ g_colour;  // upstream grads (nullable)
+  const float* __restrict__ g_depth;
+  const float* __restrict__ g_acc;
+  const float* __restrict__ g_disp;
+  float* __restrict__ gdens;  // outputs (nullable)
+  float* __restrict__ gfeat;
+};
+
+struct RayCtx {
+  Ray r;
+  float dnorm;
+  DepthGen dg;
+  int i_lo, i_hi;
+};
+
+__device__ __forceinline__ void setup_ray(const GridP& g, const RaysP& rp, const CfgP& c, long long ray, RayCtx& s,
+                                          float& vx, float& vy, float& vz) {
+  s.r = load_ray(rp, ray);
+  const Ray& r = s.r;
+  // ||d||: accumulate.py:55 / process.py:53
+  s.dnorm = sqrtf(fmaf(r.dz, r.dz, fmaf(r.dy, r.dy, r.dx * r.dx)));
+  vx = __fdiv_rn(r.dx, s.dnorm), vy = __fdiv_rn(r.dy, s.dnorm), vz = __fdiv_rn(r.dz, s.dnorm);
+  float near = c.near, far = c.far;
+  if (rp.bounds) {
+    near = __ldg(rp.bounds + 2 * ray), far = __ldg(rp.bounds + 2 * ray + 1);
+  } else if (c.flags & R3D_FLAG_OPTIMIZED_SAMPLING) {
+    reference_aabb_bounds(g, r, c.near, c.far, near, far);
+  }
+  s.dg.near = near, s.dg.far = far;
+  s.dg.S = c.S, s.dg.half = c.S / 2;
+  s.dg.step = c.S > 1 ? __fdiv_rn(1.0f, (float)(c.S - 1)) : 0.0f;
+  s.dg.perturb = (c.flags & R3D_FLAG_PERTURB) != 0;
+  s.dg.jit = c.jitter ? c.jitter + (size_t)ray * c.S : nullptr;
+  s.dg.key = ray_rng_key(c.seed_lo, c.seed_hi, ray);
+  sample_range(g, r, near, far, c.S, s.i_lo, s.i_hi);
+}
+
+// ---- per-corner SH record contraction (forward) -------------------------------------------------
+template <int DEG, bool VEC>
+__device__ __forceinline__ void corner_radiance(const float* __restrict__ rec, const float (&Y)[(DEG + 1) * (DEG + 1)],
+                                                bool diffuse, float w, float& r, float& g, float& b) {
+  constexpr int K = (DEG + 1) * (DEG + 1);
+  constexpr int F = 3 * K;
+  if (DEG > 0 && diffuse) {  // SH band 0 only (process.py:59-63)
+    const float wy = w * Y[0];
+    r = fmaf(wy, __ldg(rec), r);
+    g = fmaf(wy, __ldg(rec + K), g);
+    b = fmaf(wy, __ldg(rec + 2 * K), b);
+    return;
+  }
+  constexpr int NV = (F + 3) / 4;
+  float v[NV * 4];
+  if constexpr (VEC) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(rec) + j);
+      v[4 * j] = q.x, v[4 * j + 1] = q.y, v[4 * j + 2] = q.z, v[4 * j + 3] = q.w;
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < F; ++e) v[e] = __ldg(rec + e);
+  }
+  float sr = 0.f, sg = 0.f, sb = 0.f;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    sr = fmaf(Y[k], v[k], sr);
+    sg = fmaf(Y[k], v[K + k], sg);
+    sb = fmaf(Y[k], v[2 * K + k], sb);
+  }
+  r = fmaf(w, sr, r), g = fmaf(w, sg, g), b = fmaf(w, sb, b);
+}
+
+template <int DEG, bool VEC>
+__device__ __forceinline__ void gather_radiance(const GridP& g, const Cell& c, const float (&Y)[(DEG + 1) * (DEG + 1)],
+                                                bool diffuse, float& rr, float& rg, float& rb) {
+  rr = rg = rb = 0.f;
+#pragma unroll
+  for (int ix = 0; ix < 2; ++ix)
+#pragma unroll
+    for (int iy = 0; iy < 2; ++iy) {
+      const float wxy = c.wx[ix] * c.wy[iy];
+      const size_t col = (size_t)(c.ox[ix] + c.oy[iy]);
+#pragma unroll
+      for (int iz = 0; iz < 2; ++iz) {
+        const float w = wxy * c.wz[iz];
+        corner_radiance<DEG, VEC>(g.feat + (col + c.oz[iz]) * (size_t)g.stride, Y, diffuse, w, rr, rg, rb);
+      }
+    }
+}
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// ---- per-corner gradient scatter (backward) -----------------------------------------------------
+// d coeff[ch][k] = Y_k * d raw_ch (SH is linear), times the corner's trilinear weight.
+template <int DEG, bool VEC>
+__device__ __forceinline__ void corner_scatter(float* __restrict__ rec, const float (&Y)[(DEG + 1) * (DEG + 1)],
+                                               bool diffuse, float w, const float (&draw)[3]) {
+  constexpr int K = (DEG + 1) * (DEG + 1);
+  constexpr int F = 3 * K;
+  const float wd[3] = {w * draw[0], w * draw[1], w * draw[2]};
+  if (DEG > 0 && diffuse) {
+    atomicAdd(rec, wd[0] * Y[0]);
+    atomicAdd(rec + K, wd[1] * Y[0]);
+    atomicAdd(rec + 2 * K, wd[2] * Y[0]);
+    return;
+  }
+  if constexpr (VEC) {
+    constexpr int NV = (F + 3) / 4;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      float q[4];
+#pragma unroll
+      for (int l = 0; l < 4; ++l) {
+        const int e = 4 * j + l;
+        q[l] = (e < F) ? wd[e / K] * Y[e % K] : 0.0f;
+      }
+      red_add_v4(rec + 4 * j, q[0], q[1], q[2], q[3]);
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < F; ++e) atomicAdd(rec + e, wd[e / K] * Y[e % K]);
+  }
+}
+
+// =================================================================================================
+// forward
+// =================================================================================================
+template <int DEG, bool VEC>
+__global__ void __launch_bounds__(128) render_fwd_kernel(const GridP g, const RaysP rp, const CfgP c, const OutP out) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long ray = thread_to_ray(rp, t);
+  if (ray < 0) return;
+
+  RayCtx s;
+  float vx, vy, vz;
+  setup_ray(g, rp, c, ray, s, vx, vy, vz);
+  constexpr int K = (DEG + 1) * (DEG + 1);
+  float Y[K];
+  sh_basis<DEG>(vx, vy, vz, Y);
+  const bool diffuse = (c.flags & R3D_FLAG_DIFFUSE) != 0;
+  const Ray& r = s.r;
+
+  float T = 1.0f, cr = 0.f, cg = 0.f, cb = 0.f, dep = 0.f, acc = 0.f;
+  if (s.i_lo <= s.i_hi) {
+    float z = s.dg.at(s.i_lo);
+    for (int i = s.i_lo; i <= s.i_hi; ++i) {
+      const bool last = (i == c.S - 1);
+      const float zn = last ? 0.0f : s.dg.at(i + 1);
+      const float px = __fadd_rn(r.ox, __fmul_rn(r.dx, z));  // sample.py:67
+      const float py = __fadd_rn(r.oy, __fmul_rn(r.dy, z));
+      const float pz = __fadd_rn(r.oz, __fmul_rn(r.dz, z));
+      if (inside_aabb(g, px, py, pz)) {
+        Cell cell;
+        make_cell(g, px, py, pz, cell);
+        float dpost;
+        const float sigma = density_post(g.post, density_pre_interp(g, cell), dpost);
+        if (sigma != 0.0f) {
+          // accumulate.py:49-55, :24-28
+          const float delta = last ? __fmul_rn(kInfinity, s.dnorm) : __fmul_rn(__fsub_rn(zn, z), s.dnorm);
+          const float alpha = 1.0f - expf(-(sigma * delta));
+          const float w = alpha * T;
+          float rr, rg, rb;
+          gather_radiance<DEG, VEC>(g, cell, Y, diffuse, rr, rg, rb);
+          cr = fmaf(w, sigmoidf_(rr), cr);
+          cg = fmaf(w, sigmoidf_(rg), cg);
+          cb = fmaf(w, sigmoidf_(rb), cb);
+          dep = fmaf(w, z, dep);
+          acc += w;
+          T *= (1.0f - alpha);
+          if (T == 0.0f) break;  // every later weight is alpha*0 = 0 exactly
+        }
+      }
+      z = zn;
+    }
+  }
+  if (c.flags & R3D_FLAG_WHITE_BKGD) {  // accumulate.py:77-81
+    const float bg = 1.0f - acc;
+    cr += bg, cg += bg, cb += bg;
+  }
+  out.colour[3 * ray] = cr, out.colour[3 * ray + 1] = cg, out.colour[3 * ray + 2] = cb;
+  out.depth[ray] = dep;
+  out.acc[ray] = acc;
+  if (out.disparity) {  // accumulate.py:85-88; 0/0 stays NaN through torch.maximum
+    const float ratio = __fdiv_rn(dep, acc);
+    const float m = (ratio != ratio) ? ratio : fmaxf(kZeroPlus, ratio);
+    out.disparity[ray] = __fdiv_rn(1.0f, m);
+  }
+}
+
+// =================================================================================================
+// backward
+// =================================================================================================
+template <int DEG, bool VEC>
+__global__ void __launch_bounds__(128) render_bwd_kernel(const GridP g, const RaysP rp, const CfgP c, const BwdP b) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long ray = thread_to_ray(rp, t);
+  if (ray < 0) return;
+
+  // ---- per-ray upstream gradients ----
+  float gc[3] = {0.f, 0.f, 0.f}, gd = 0.f, ga = 0.f;
+  if (b.g_colour) gc[0] = __ldg(b.g_colour + 3 * ray), gc[1] = __ldg(b.g_colour + 3 * ray + 1), gc[2] = __ldg(b.g_colour + 3 * ray + 2);
+  if (b.g_depth) gd = __ldg(b.g_depth + ray);
+  if (b.g_acc) ga = __ldg(b.g_acc + ray);
+  const float acc_f = __ldg(b.acc + ray), dep_f = __ldg(b.depth + ray);
+  if (b.g_disp) {
+    // disparity = 1 / max(eps, depth/acc) (accumulate.py:85-88): acc/depth when depth/acc > eps
+    const float gdisp = __ldg(b.g_disp + ray);
+    if (gdisp != 0.0f) {
+      const float ratio = __fdiv_rn(dep_f, acc_f);
+      if (ratio != ratio) {
+        gd = ga = ratio;  // the reference back-propagates NaN through 0/0
+      } else if (ratio > kZeroPlus) {
+        const float disp = __fdiv_rn(1.0f, ratio);
+        gd = fmaf(gdisp, -disp * disp / acc_f, gd);
+        ga = fmaf(gdisp, disp / acc_f, ga);
+      }
+    }
+  }
+  float cfr = __ldg(b.colour + 3 * ray), cfg_ = __ldg(b.colour + 3 * ray + 1), cfb = __ldg(b.colour + 3 * ray + 2);
+  if (c.flags & R3D_FLAG_WHITE_BKGD) {
+    const float bg = 1.0f - acc_f;
+    cfr -= bg, cfg_ -= bg, cfb -= bg;
+    ga -= (gc[0] + gc[1] + gc[2]);  // d(1 - acc)/d acc on every channel
+  }
+  const float total = fmaf(gc[0], cfr, fmaf(gc[1], cfg_, fmaf(gc[2], cfb, fmaf(gd, dep_f, ga * acc_f))));
+  if (gc[0] == 0.f && gc[1] == 0.f && gc[2] == 0.f && gd == 0.f && ga == 0.f) return;
+
+  RayCtx s;
+  float vx, vy, vz;
+  setup_ray(g, rp, c, ray, s, vx, vy, vz);
+  constexpr int K = (DEG + 1) * (DEG + 1);
+  float Y[K];
+  sh_basis<DEG>(vx, vy, vz, Y);
+  const bool diffuse = (c.flags & R3D_FLAG_DIFFUSE) != 0;
+  const Ray& r = s.r;
+  const float dmul = (g.pre == R3D_PRE_ABS) ? fabsf(g.dscale) : g.dscale;
+
+  float T = 1.0f, prefix = 0.f;
+  if (s.i_lo > s.i_hi) return;
+  // |q_i| <= |g_c|_1 + |g_d| z_max + |g_a|  (z is monotone and non-negative along the marched range)
+  const float qmax = fabsf(gc[0]) + fabsf(gc[1]) + fabsf(gc[2]) + fabsf(gd) * fmaxf(fabsf(s.dg.near), fabsf(s.dg.far)) + fabsf(ga);
+  float z = s.dg.at(s.i_lo);
+  for (int i = s.i_lo; i <= s.i_hi; ++i) {
+    const bool last = (i == c.S - 1);
+    const float zn = last ? 0.0f : s.dg.at(i + 1);
+    const float px = __fadd_rn(r.ox, __fmul_rn(r.dx, z));
+    const float py = __fadd_rn(r.oy, __fmul_rn(r.dy, z));
+    const float pz = __fadd_rn(r.oz, __fmul_rn(r.dz, z));
+    if (inside_aabb(g, px, py, pz)) {
+      Cell cell;
+      make_cell(g, px, py, pz, cell);
+      float dpost;
+      const float sigma = density_post(g.post, density_pre_interp(g, cell), dpost);
+      if (sigma != 0.0f || dpost != 0.0f) {
+        const float delta = last ? __fmul_rn(kInfinity, s.dnorm) : __fmul_rn(__fsub_rn(zn, z), s.dnorm);
+        const float alpha = 1.0f - expf(-(sigma * delta));
+        const float w = alpha * T;
+        const float Tn = T * (1.0f - alpha);
+        float rr, rg, rb;
+        gather_radiance<DEG, VEC>(g, cell, Y, diffuse, rr, rg, rb);
+        const float sr = sigmoidf_(rr), sg = sigmoidf_(rg), sb = sigmoidf_(rb);
+        const float q = fmaf(gc[0], sr, fmaf(gc[1], sg, fmaf(gc[2], sb, fmaf(gd, z, ga))));
+        prefix = fmaf(w, q, prefix);
+        // sum_{j>i} w_j q_j = total - prefix.  It is empty for the last sample and once the transmittance is exactly 0.
+        // The subtraction carries the rounding residue of two O(|total|) numbers (~6e-8 |total|); the true value is
+        // bounded by T_{i+1} * max|q| (the later weights sum to at most T_{i+1}, sigmoid <= 1), so it is clamped to
+        // that bound: deep inside opaque matter the residue would otherwise dwarf the (vanishing) true gradient.
+        float suffix = 0.0f;
+        if (!last && Tn != 0.0f) {
+          const float bound = Tn * qmax;
+          suffix = fminf(fmaxf(total - prefix, -bound), bound);
+        }
+        const float dsigma = delta * (Tn * q - suffix);
+        const float dpre = dsigma * dpost * dmul;
+        const float draw[3] = {w * gc[0] * sr * (1.0f - sr), w * gc[1] * sg * (1.0f - sg), w * gc[2] * sb * (1.0f - sb)};
+        const bool feat_grad = b.gfeat && (draw[0] != 0.f || draw[1] != 0.f || draw[2] != 0.f);
+#pragma unroll
+        for (int ix = 0; ix < 2; ++ix)
+#pragma unroll
+          for (int iy = 0; iy < 2; ++iy) {
+            const float wxy = cell.wx[ix] * cell.wy[iy];
+            const size_t col = (size_t)(cell.ox[ix] + cell.oy[iy]);
+#pragma unroll
+            for (int iz = 0; iz < 2; ++iz) {
+              const float wc = wxy * cell.wz[iz];
+              if (wc == 0.0f) continue;  // out-of-range (zero padding) or exactly-on-plane corner
+              const size_t vox = col + cell.oz[iz];
+              if (b.gdens && dpre != 0.0f) {
+                float gv = wc * dpre;
+                if (g.pre == R3D_PRE_ABS) {
+                  const float v = __ldg(g.dens + vox);
+                  gv = (v > 0.f) ? gv : ((v < 0.f) ? -gv : 0.0f);  // d|x|/dx = sign(x), 0 at 0 (torch.abs)
+                }
+                atomicAdd(b.gdens + vox, gv);
+              }
+              if (feat_grad) corner_scatter<DEG, VEC>(b.gfeat + vox * (size_t)g.stride, Y, diffuse, wc, draw);
+            }
+          }
+        T = Tn;
+        if (T == 0.0f) break;
+      }
+    }
+    z = zn;
+  }
+}
+
+// =================================================================================================
+// measurement helper: mark voxels referenced as interpolation corners by in-volume samples
+// =================================================================================================
+__global__ void __launch_bounds__(128) mark_touched_kernel(const GridP g, const RaysP rp, const CfgP c, uint8_t* __restrict__ bitmap) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long ray = thread_to_ray(rp, t);
+  if (ray < 0) return;
+  RayCtx s;
+  float vx, vy, vz;
+  setup_ray(g, rp, c, ray, s, vx, vy, vz);
+  const Ray& r = s.r;
+  for (int i = s.i_lo; i <= s.i_hi; ++i) {
+    const float z = s.dg.at(i);
+    const float px = __fadd_rn(r.ox, __fmul_rn(r.dx, z));
+    const float py = __fadd_rn(r.oy, __fmul_rn(r.dy, z));
+    const float pz = __fadd_rn(r.oz, __fmul_rn(r.dz, z));
+    if (!inside_aabb(g, px, py, pz)) continue;
+    Cell cell;
+    make_cell(g, px, py, pz, cell);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int ix = k >> 2, iy = (k >> 1) & 1, iz = k & 1;
+      if (cell.wx[ix] * cell.wy[iy] * cell.wz[iz] != 0.0f) bitmap[(size_t)(cell.ox[ix] + cell.oy[iy] + cell.oz[iz])] = 1;
+    }
+  }
+}
+
+// =================================================================================================
+// host-side dispatch
+// =================================================================================================
+template <int DEG>
+static void launch_fwd(bool vec, dim3 grid, cudaStream_t st, const GridP& g, const RaysP& r, const CfgP& c, const OutP& o) {
+  if (vec)
+    render_fwd_kernel<DEG, true><<<grid, 128, 0, st>>>(g, r, c, o);
+  else
+    render_fwd_kernel<DEG, false><<<grid, 128, 0, st>>>(g, r, c, o);
+}
+template <int DEG>
+static void launch_bwd(bool vec, dim3 grid, cudaStream_t st, const GridP& g, const RaysP& r, const CfgP& c, const BwdP& b) {
+  if (vec)
+    render_bwd_kernel<DEG, true><<<grid, 128, 0, st>>>(g, r, c, b);
+  else
+    render_bwd_kernel<DEG, false><<<grid, 128, 0, st>>>(g, r, c, b);
+}
+
+static int grid_blocks(const RaysP& r, dim3& grid) {
+  const long long threads = threads_for_rays(r.n, r.tile_w, r.tile_h);
+  const long long blocks = (threads + 127) / 128;
+  if (blocks > 0x7fffffffLL) return fail(R3D_ERR_UNSUPPORTED, "too many rays for one launch (%lld)", (long long)r.n);
+  grid = dim3((unsigned)blocks);
+  return R3D_OK;
+}
+
+}  // namespace r3d
+
+using namespace r3d;
+
+extern "C" int r3d_render_fwd(const R3dGrid* grid, const R3dRays* rays, const R3dRenderConfig* cfg, const R3dRenderOut* out,
+                              void* cuda_stream) {
+  GridP g;
+  RaysP r;
+  CfgP c;
+  int rc;
+  if ((rc = to_device_params(grid, g)) || (rc = to_device_params(rays, r)) || (rc = to_device_params(cfg, r, c))) return rc;
+  if (r.n == 0) return R3D_OK;
+  if (!out || !out->colour || !out->depth || !out->acc) return fail(R3D_ERR_INVALID_ARGUMENT, "render output buffers are NULL");
+  OutP o{out->colour, out->depth, out->acc, out->disparity};
+  dim3 blocks;
+  if ((rc = grid_blocks(r, blocks))) return rc;
+  const bool vec = (g.stride % 4 == 0) && aligned16(g.feat);
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  switch (grid->sh_degree) {
+    case 0: launch_fwd<0>(vec, blocks, st, g, r, c, o); break;
+    case 1: launch_fwd<1>(vec, blocks, st, g, r, c, o); break;
+    case 2: launch_fwd<2>(vec, blocks, st, g, r, c, o); break;
+    default: launch_fwd<3>(vec, blocks, st, g, r, c, o); break;
+  }
+  return check_launch("r3d_render_fwd");
+}
+
+extern "C" int r3d_render_bwd(const R3dGrid* grid, const R3dRays* rays, const R3dRenderConfig* cfg, const R3dRenderOut* saved,
+                              const R3dRenderOutGrad* grad_out, const R3dGridGrad* grad_grid, void* cuda_stream) {
+  GridP g;
+  RaysP r;
+  CfgP c;
+  int rc;
+  if ((rc = to_device_params(grid, g)) || (rc = to_device_params(rays, r)) || (rc = to_device_params(cfg, r, c))) return rc;
+  if (r.n == 0) return R3D_OK;
+  if (!saved || !saved->colour || !saved->depth || !saved->acc)
+    return fail(R3D_ERR_INVALID_ARGUMENT, "saved forward outputs (colour, depth, acc) are required by the backward pass");
+  if (!grad_out || !grad_grid) return fail(R3D_ERR_INVALID_ARGUMENT, "grad_out / grad_grid is NULL");
+  if (!grad_grid->densities && !grad_grid->features) return R3D_OK;
+  BwdP b{saved->colour,   saved->depth,       saved->acc,           grad_out->colour, grad_out->depth,
+         grad_out->acc,   grad_out->disparity, grad_grid->densities, grad_grid->features};
+  dim3 blocks;
+  if ((rc = grid_blocks(r, blocks))) return rc;
+  const bool vec = (g.stride % 4 == 0) && aligned16(g.feat) && aligned16(b.gfeat);
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  switch (grid->sh_degree) {
+    case 0: launch_bwd<0>(vec, blocks, st, g, r, c, b); break;
+    case 1: launch_bwd<1>(vec, blocks, st, g, r, c, b); break;
+    case 2: launch_bwd<2>(vec, blocks, st, g, r, c, b); break;
+    default: launch_bwd<3>(vec, blocks, st, g, r, c, b); break;
+  }
+  return check_launch("r3d_render_bwd");
+}
+
+extern "C" int r3d_mark_touched_voxels(const R3dGrid* grid, const R3dRays* rays, const R3dRenderConfig* cfg, uint8_t* bitmap,
+                                       void* cuda_stream) {
+  GridP g;
+  RaysP r;
+  CfgP c;
+  int rc;
+  if ((rc = to_device_params(grid, g)) || (rc = to_device_params(rays, r)) || (rc = to_device_params(cfg, r, c))) return rc;
+  if (!bitmap) return fail(R3D_ERR_INVALID_ARGUMENT, "bitmap is NULL");
+  if (r.n == 0) return R3D_OK;
+  dim3 blocks;
+  if ((rc = grid_blocks(r, blocks))) return rc;
+  mark_touched_kernel<<<blocks, 128, 0, static_cast<cudaStream_t>(cuda_stream)>>>(g, r, c, bitmap);
+  return check_launch("r3d_mark_touched_voxels");
+}

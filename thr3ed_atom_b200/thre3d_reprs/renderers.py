@@ -1,0 +1,191 @@
+"""The SH voxel-grid render procedure -- the drop-in for the reference's
+``thre3d_atom/thre3d_reprs/renderers.py`` (``RenderProcedure`` :25, ``SHVoxGridRenderConfig`` :28-45,
+``render_sh_voxel_grid`` :48-102).
+
+The reference binds three ``functools.partial`` stages (sampler, point processor, accumulator) and
+lets autograd differentiate ~150 ATen launches over materialised ``[N*S, F+1]`` tensors.  Here the
+same procedure is ONE fused CUDA kernel forward and ONE fused kernel backward behind the C ABI
+(``include/r3d_b200.h``); per-ray state lives in registers, nothing of size ``N*S`` is ever stored.
+
+``SHVoxGridRenderConfig`` keeps the reference's fields, order and defaults (it is pickled by
+qualified name and rebuilt from ``dataclasses.asdict`` when checkpoints are loaded).
+"""
+from __future__ import annotations
+
+import contextlib
+import dataclasses
+import threading
+from typing import Any, Callable, Optional, Tuple
+
+import torch
+from torch import Tensor
+from torch.nn import Module
+
+from thr3ed_atom_b200 import _kernels
+from thr3ed_atom_b200.rendering.volumetric.accumulate import density2occupancy_pb
+from thr3ed_atom_b200.rendering.volumetric.render_interface import Rays, RenderOut, assert_flat_rays
+from thr3ed_atom_b200.thre3d_reprs.voxels import VoxelGrid
+from thr3ed_atom_b200.utils.constants import EXTRA_ACCUMULATED_WEIGHTS, EXTRA_DISPARITY
+from thr3ed_atom_b200.utils.imaging_utils import CameraBounds
+
+RenderConfig = Any
+RenderProcedure = Callable[[Module, Rays, RenderConfig, Optional[int]], RenderOut]
+
+
+@dataclasses.dataclass
+class SHVoxGridRenderConfig:
+    # probing
+    num_samples_per_ray: int
+    camera_bounds: CameraBounds
+    perturb_sampled_points: bool = True
+    optimized_sampling: bool = False
+
+    # accumulation
+    density2occupancy: Callable[[Tensor, Tensor], Tensor] = density2occupancy_pb
+    radiance_hdr_tone_map: Callable[[Tensor], Tensor] = torch.sigmoid
+    stochastic_density_noise_std: float = 0.0
+    white_bkgd: bool = False
+
+    # misc render modes (consumed by the callers)
+    render_diffuse: bool = False
+    render_num_samples_per_ray: int = 1024
+    parallel_rays_chunk_size: int = 32768
+
+
+# ---------------------------------------------------------------------------------------------
+# per-call hints that have no slot in the reference's config dataclass
+# ---------------------------------------------------------------------------------------------
+_hints = threading.local()
+
+
+@contextlib.contextmanager
+def render_hints(*, image_hw: Optional[Tuple[int, int]] = None, jitter: Optional[Tensor] = None, rng_seed: Optional[int] = None, variant: Optional[int] = None):
+    """Optional side-channel for ``render_sh_voxel_grid`` calls made inside the ``with`` block.
+
+    image_hw: the flat rays are a row-major ``H x W`` image -> threads are mapped to 8x4 pixel tiles
+              (pure scheduling hint; per-ray results are unchanged).
+    jitter:   explicit ``[N, S]`` stratified offsets in ``[0, 1)`` (what the reference draws with
+              ``torch.rand``) instead of the in-kernel counter-based RNG; used for parity tests.
+    rng_seed: seed of the in-kernel RNG (default: drawn from torch's CPU generator, so
+              ``torch.manual_seed`` makes renders reproducible).
+    variant:  kernel variant selector (A/B measurement only).
+    """
+    previous = getattr(_hints, "value", None)
+    _hints.value = {"image_hw": image_hw, "jitter": jitter, "rng_seed": rng_seed, "variant": variant}
+    try:
+        yield
+    finally:
+        _hints.value = previous
+
+
+def _current_hints() -> dict:
+    return getattr(_hints, "value", None) or {}
+
+
+# ---------------------------------------------------------------------------------------------
+# autograd binding of the fused kernels
+# ---------------------------------------------------------------------------------------------
+class _FusedSHVoxGridRender(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, densities: Tensor, features: Tensor, origins: Tensor, directions: Tensor, grid: VoxelGrid, args: _kernels.RenderArgs):
+        desc = grid.kernel_desc(densities, features)
+        colour, depth, acc, disparity = _kernels.render_forward(desc, origins, directions, args)
+        ctx.desc, ctx.args = desc, args
+        ctx.save_for_backward(origins, directions, colour, depth, acc)
+        ctx.set_materialize_grads(False)  # unused outputs arrive as None instead of zero tensors
+        return colour, depth, acc, disparity
+
+    @staticmethod
+    def backward(ctx, g_colour, g_depth, g_acc, g_disparity):
+        origins, directions, colour, depth, acc = ctx.saved_tensors
+        desc = ctx.desc
+        need_d, need_f = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        grad_d = torch.zeros_like(desc.densities) if need_d else None
+        grad_f = torch.zeros_like(desc.features) if need_f else None
+        if need_d or need_f:
+            _kernels.render_backward(
+                desc, origins, directions, ctx.args, (colour, depth, acc), (g_colour, g_depth, g_acc, g_disparity), grad_d, grad_f
+            )
+        return grad_d, grad_f, None, None, None, None
+
+
+def _validate_config(cfg: SHVoxGridRenderConfig) -> None:
+    # the fused kernels implement exactly the reference defaults of the accumulation stage; anything else is refused loudly
+    if cfg.density2occupancy is not density2occupancy_pb and getattr(cfg.density2occupancy, "__name__", "") != "density2occupancy_pb":
+        raise NotImplementedError("only density2occupancy_pb (1 - exp(-sigma * delta)) is implemented by the fused B200 renderer")
+    if cfg.radiance_hdr_tone_map is not torch.sigmoid:
+        raise NotImplementedError("only torch.sigmoid is implemented as radiance_hdr_tone_map by the fused B200 renderer")
+    if cfg.stochastic_density_noise_std != 0.0:
+        raise NotImplementedError("stochastic_density_noise_std != 0 is not implemented by the fused B200 renderer")
+
+
+def _draw_seed() -> int:
+    # consumes torch's default CPU generator => reproducible under torch.manual_seed
+    return int(torch.randint(0, 2**62, (1,), dtype=torch.int64).item())
+
+
+def make_render_args(cfg: SHVoxGridRenderConfig, **overrides) -> _kernels.RenderArgs:
+    hints = _current_hints()
+    near, far = cfg.camera_bounds
+    args = _kernels.RenderArgs(
+        num_samples=int(cfg.num_samples_per_ray),
+        near=float(near),
+        far=float(far),
+        perturb=bool(cfg.perturb_sampled_points),
+        white_bkgd=bool(cfg.white_bkgd),
+        diffuse=bool(cfg.render_diffuse),
+        optimized_sampling=bool(cfg.optimized_sampling),
+        jitter=hints.get("jitter"),
+        image_hw=hints.get("image_hw"),
+        variant=hints.get("variant") or 0,
+    )
+    if args.perturb and args.jitter is None:
+        seed = hints.get("rng_seed")
+        args.rng_seed = _draw_seed() if seed is None else int(seed)
+    for k, v in overrides.items():
+        setattr(args, k, v)
+    return args
+
+
+def render_sh_voxel_grid(
+    voxel_grid: VoxelGrid,
+    rays: Rays,
+    render_config: SHVoxGridRenderConfig,
+    parallel_points_chunk_size: Optional[int] = None,
+) -> RenderOut:
+    """
+    renders an SH-based voxel grid
+    Args:
+        voxel_grid: the VoxelGrid being rendered
+        rays: flat ``[N, 3]`` rays (origins + not-necessarily-unit directions) on the grid's device
+        render_config: SHVoxGridRenderConfig
+        parallel_points_chunk_size: memory hint of the reference's op-by-op pipeline; the fused kernel keeps
+            per-ray state in registers and needs no chunking, so it is accepted and ignored
+    Returns: RenderOut(colour [N,3], depth [N,1], extra={disparity [N,1], accumulated_weight [N,1]}),
+             differentiable w.r.t. the grid's densities / features when grad mode is on
+    """
+    assert_flat_rays(rays)
+    _validate_config(render_config)
+    args = make_render_args(render_config)
+    if args.image_hw is not None and args.image_hw[0] * args.image_hw[1] != rays.origins.shape[0]:
+        args.image_hw = None  # hint does not describe this batch (e.g. a chunk of an image)
+    origins = rays.origins.detach().contiguous()
+    directions = rays.directions.detach().contiguous()
+    colour, depth, acc, disparity = _FusedSHVoxGridRender.apply(
+        voxel_grid.densities, voxel_grid.feature_storage, origins, directions, voxel_grid, args
+    )
+    return RenderOut(colour=colour, depth=depth, extra={EXTRA_DISPARITY: disparity, EXTRA_ACCUMULATED_WEIGHTS: acc})
+
+
+def render_sh_voxel_grid_camera(voxel_grid: VoxelGrid, camera_intrinsics, camera_pose, render_config: SHVoxGridRenderConfig) -> RenderOut:
+    """Whole-image inference render with IN-KERNEL ray generation (no ray tensors, no chunking):
+    the fused form of ``cast_rays`` + ``flatten_rays`` + ``render_sh_voxel_grid`` used by
+    ``VolumetricModel.render``.  Not differentiable (the reference's ``render`` runs under no_grad)."""
+    _validate_config(render_config)
+    height, width, focal = camera_intrinsics
+    rot = torch.as_tensor(camera_pose.rotation).detach().to("cpu", torch.float32).reshape(9).tolist()
+    trans = torch.as_tensor(camera_pose.translation).detach().to("cpu", torch.float32).reshape(3).tolist()
+    args = make_render_args(render_config, camera=(int(height), int(width), float(focal), rot, trans), image_hw=None)
+    with torch.no_grad():
+        colour, depth, acc, disparity = _kernels.render_forward(voxel_grid.kernel_desc(), None, None, args)
+    return RenderOut(colour=colour, depth=depth, extra={EXTRA_DISPARITY: disparity, EXTRA_ACCUMULATED_WEIGHTS: acc})

@@ -1,0 +1,349 @@
+"""Dense voxel grid (density + SH features) backed by the B200 kernels.
+
+API mirror of the reference's ``thre3d_atom/thre3d_reprs/voxels.py`` (``VoxelGrid`` :46-331,
+``scale_voxel_grid_with_required_output_size`` :334-373, ``create_voxel_grid_from_saved_info_dict``
+:376-383) with a storage layout chosen for the kernels:
+
+* ``_densities``  ``[W, D, H, 1]`` fp32 -- the reference's layout unchanged: a 4 B/voxel volume the
+  kernels probe first (it stays L2-resident up to ~256^3), so empty space never touches features.
+* ``_features``   ``[W, D, H, stride]`` fp32 with ``stride = F`` rounded up to a multiple of 4, so every
+  voxel record is a whole number of 16-byte vectors (deg 0: 3->4, deg 1: 12, deg 2: 27->28, deg 3: 48)
+  and is read/updated with 128-bit loads and ``red.global.add.v4.f32``.  The padding lane is never
+  read by the maths and only ever receives zero gradient.
+
+The public surface hides the padding: ``.features`` is a ``[..., :F]`` view, ``state_dict()`` emits and
+``load_state_dict()`` accepts the reference's ``_densities`` / ``_features`` shapes, and the setters
+take reference-shaped tensors.
+"""
+from __future__ import annotations
+
+from typing import Any, Callable, Dict, NamedTuple, Optional, Tuple
+
+import torch
+from torch import Tensor
+from torch.nn import Module
+from torch.nn.functional import interpolate
+
+from thr3ed_atom_b200 import _abi, _kernels
+from thr3ed_atom_b200.thre3d_reprs.constants import CONFIG_DICT, STATE_DICT, THRE3D_REPR, u_DENSITIES, u_FEATURES
+from thr3ed_atom_b200.utils.imaging_utils import range_map_coefficients
+
+
+class VoxelSize(NamedTuple):
+    """edge lengths of one voxel along x, y, z (anisotropic voxels allowed)"""
+
+    x_size: float = 1.0
+    y_size: float = 1.0
+    z_size: float = 1.0
+
+
+class VoxelGridLocation(NamedTuple):
+    """world-space position of the grid centre; the grid is axis aligned"""
+
+    x_coord: float = 0.0
+    y_coord: float = 0.0
+    z_coord: float = 0.0
+
+
+class AxisAlignedBoundingBox(NamedTuple):
+    x_range: Tuple[float, float]
+    y_range: Tuple[float, float]
+    z_range: Tuple[float, float]
+
+
+def padded_feature_stride(num_features: int) -> int:
+    return (num_features + 3) // 4 * 4
+
+
+def _is_identity(fn) -> bool:
+    return isinstance(fn, torch.nn.Identity)
+
+
+def classify_density_activations(pre: Callable, post: Callable) -> Tuple[int, int]:
+    """Map the (pre, post) density activation callables onto the kernel enums.
+
+    Supported = the three fields the reference's train script can build
+    (train_sh_based_voxel_grid_with_posed_images.py:169-192): ReLU field (Identity, ReLU), softplus
+    field (Identity, Softplus) and the traditional field (abs, Identity) -- plus their cross products.
+    Anything else raises: the fused path never silently substitutes semantics.
+    """
+    if _is_identity(pre):
+        pre_id = _abi.PRE_IDENTITY
+    elif pre is torch.abs or pre is Tensor.abs:
+        pre_id = _abi.PRE_ABS
+    else:
+        raise NotImplementedError(f"density_preactivation {pre!r} is not supported by the fused B200 kernels (Identity | torch.abs)")
+    if _is_identity(post):
+        post_id = _abi.POST_IDENTITY
+    elif isinstance(post, torch.nn.ReLU) or post is torch.relu or post is torch.nn.functional.relu:
+        post_id = _abi.POST_RELU
+    elif (isinstance(post, torch.nn.Softplus) and post.beta in (1, 1.0) and post.threshold in (20, 20.0)) or post is torch.nn.functional.softplus:
+        post_id = _abi.POST_SOFTPLUS
+    else:
+        raise NotImplementedError(
+            f"density_postactivation {post!r} is not supported by the fused B200 kernels (Identity | ReLU | Softplus(beta=1, threshold=20))"
+        )
+    return pre_id, post_id
+
+
+class _GridLookup(torch.autograd.Function):
+    """``VoxelGrid.forward`` on free points: CUDA gather forward, CUDA scatter backward."""
+
+    @staticmethod
+    def forward(ctx, densities: Tensor, features: Tensor, points: Tensor, grid: "VoxelGrid") -> Tensor:
+        desc = grid.kernel_desc(densities, features)
+        out, _ = _kernels.grid_lookup_forward(desc, points)
+        ctx.grid, ctx.desc = grid, desc
+        ctx.save_for_backward(points)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out: Tensor):
+        (points,) = ctx.saved_tensors
+        desc = ctx.desc
+        g_d = torch.zeros_like(desc.densities) if ctx.needs_input_grad[0] else None
+        g_f = torch.zeros_like(desc.features) if ctx.needs_input_grad[1] else None
+        if g_d is not None or g_f is not None:
+            _kernels.grid_lookup_backward(desc, points, grad_out, g_d, g_f)
+        return g_d, g_f, None, None
+
+
+class VoxelGrid(Module):
+    def __init__(
+        self,
+        densities: Tensor,
+        features: Tensor,
+        voxel_size: VoxelSize,
+        grid_location: Optional[VoxelGridLocation] = VoxelGridLocation(),
+        density_preactivation: Callable[[Tensor], Tensor] = torch.abs,
+        density_postactivation: Callable[[Tensor], Tensor] = torch.nn.Identity(),
+        feature_preactivation: Callable[[Tensor], Tensor] = torch.nn.Identity(),
+        feature_postactivation: Callable[[Tensor], Tensor] = torch.nn.Identity(),
+        radiance_transfer_function: Callable[[Tensor, Tensor], Tensor] = None,
+        expected_density_scale: float = 1.0,
+        tunable: bool = False,
+    ):
+        """
+        Args:
+            densities: ``[W, D, H, 1]`` raw volumetric density on the grid vertices
+            features:  ``[W, D, H, F]`` features on the grid vertices (SH coefficients, channel-major)
+            voxel_size: world-space size of one voxel
+            grid_location: world-space centre of the grid
+            density_preactivation / density_postactivation: applied before / after interpolation
+            feature_preactivation / feature_postactivation: must be Identity on the fused path
+            radiance_transfer_function: optional ``(features, viewdirs) -> radiance`` used by ``forward``
+            expected_density_scale: multiplies the raw densities before the pre-activation
+            tunable: wrap densities / features in ``nn.Parameter``
+        """
+        assert len(densities.shape) == 4 and densities.shape[-1] == 1, f"densities should be of shape [W x D x H x 1] as opposed to ({densities.shape})"
+        assert len(features.shape) == 4, f"features should be of shape [W x D x H x F] as opposed to ({features.shape})"
+        assert densities.device == features.device, "densities and features are not on the same device :("
+        assert densities.shape[:3] == features.shape[:3], "densities and features disagree on the grid dimensions"
+        super().__init__()
+
+        self._density_preactivation = density_preactivation
+        self._density_postactivation = density_postactivation
+        self._feature_preactivation = feature_preactivation
+        self._feature_postactivation = feature_postactivation
+        self._radiance_transfer_function = radiance_transfer_function
+        self._grid_location = grid_location
+        self._voxel_size = voxel_size
+        self._expected_density_scale = expected_density_scale
+        self._tunable = tunable
+
+        self._num_features = int(features.shape[-1])
+        self._densities = self._wrap(self._as_storage(densities, 1))
+        self._features = self._wrap(self._as_storage(features, padded_feature_stride(self._num_features)))
+
+        self.width_x, self.depth_y, self.height_z = (int(s) for s in features.shape[:3])
+        self._aabb = self._setup_bounding_box_planes()
+        self._register_state_dict_hook(VoxelGrid._strip_padding_from_state_dict)
+
+    # ------------------------------------------------------------------ storage
+    @staticmethod
+    def _as_storage(values: Tensor, stride: int) -> Tensor:
+        """fp32 contiguous ``[W, D, H, stride]`` holding ``values`` in its first channels."""
+        values = values.detach()
+        if values.shape[-1] == stride and values.dtype == torch.float32 and values.is_contiguous():
+            return values
+        store = torch.zeros((*values.shape[:3], stride), dtype=torch.float32, device=values.device)
+        store[..., : values.shape[-1]] = values
+        return store
+
+    def _wrap(self, store: Tensor) -> Tensor:
+        return torch.nn.Parameter(store) if self._tunable else store
+
+    def _apply(self, fn, *args, **kwargs):
+        # non-tunable grids keep plain tensors (as the reference does); move them with the module too
+        super()._apply(fn, *args, **kwargs)
+        if not self._tunable:
+            self._densities, self._features = fn(self._densities), fn(self._features)
+        return self
+
+    @staticmethod
+    def _strip_padding_from_state_dict(module, state_dict, prefix, local_metadata):
+        key = prefix + u_FEATURES
+        if key in state_dict and state_dict[key].shape[-1] != module._num_features:
+            state_dict[key] = state_dict[key][..., : module._num_features].contiguous()
+        return state_dict
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        key = prefix + u_FEATURES
+        if key in state_dict and state_dict[key].shape[-1] == self._num_features != self._features.shape[-1]:
+            state_dict = dict(state_dict)
+            state_dict[key] = self._as_storage(state_dict[key], self._features.shape[-1])
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+
+    # ------------------------------------------------------------------ reference surface
+    @property
+    def densities(self) -> Tensor:
+        return self._densities
+
+    @property
+    def features(self) -> Tensor:
+        """``[W, D, H, F]`` view of the (possibly padded) feature storage; writes go through."""
+        if self._features.shape[-1] == self._num_features:
+            return self._features
+        return self._features[..., : self._num_features]
+
+    @features.setter
+    def features(self, features: Tensor) -> None:
+        assert tuple(features.shape) == (*self.grid_dims, self._num_features), "new features don't match original feature tensor's dimensions"
+        if isinstance(features, torch.nn.Parameter) and features.shape[-1] == self._features.shape[-1] and features.is_contiguous():
+            self._features = features
+        else:
+            self._features = self._wrap(self._as_storage(features, self._features.shape[-1]))
+
+    @densities.setter
+    def densities(self, densities: Tensor) -> None:
+        assert densities.shape == self._densities.shape, "new densities don't match original densities tensor's dimensions"
+        if isinstance(densities, torch.nn.Parameter) and densities.is_contiguous() and densities.dtype == torch.float32:
+            self._densities = densities
+        else:
+            self._densities = self._wrap(self._as_storage(densities, 1))
+
+    @property
+    def feature_storage(self) -> Tensor:
+        """The padded ``[W, D, H, stride]`` leaf the kernels and the optimizer work on."""
+        return self._features
+
+    @property
+    def aabb(self) -> AxisAlignedBoundingBox:
+        return self._aabb
+
+    @property
+    def grid_dims(self) -> Tuple[int, int, int]:
+        return self.width_x, self.depth_y, self.height_z
+
+    @property
+    def voxel_size(self) -> VoxelSize:
+        return self._voxel_size
+
+    @voxel_size.setter
+    def voxel_size(self, voxel_size: VoxelSize) -> None:
+        # as in the reference (voxels.py:166-168) the bounding box is NOT recomputed here
+        self._voxel_size = voxel_size
+
+    def get_config_dict(self) -> Dict[str, Any]:
+        return {
+            "grid_location": self._grid_location,
+            "density_preactivation": self._density_preactivation,
+            "density_postactivation": self._density_postactivation,
+            "feature_preactivation": self._feature_preactivation,
+            "feature_postactivation": self._feature_postactivation,
+            "radiance_transfer_function": self._radiance_transfer_function,
+            "expected_density_scale": self._expected_density_scale,
+            "tunable": self._tunable,
+        }
+
+    def get_save_config_dict(self) -> Dict[str, Any]:
+        return {**self.get_config_dict(), "voxel_size": self._voxel_size}
+
+    def _setup_bounding_box_planes(self) -> AxisAlignedBoundingBox:
+        ranges = []
+        for count, size, centre in zip(self.grid_dims, self._voxel_size, self._grid_location):
+            half = (count * size) / 2
+            ranges.append((centre - half, centre + half))
+        return AxisAlignedBoundingBox(*ranges)
+
+    def extra_repr(self) -> str:
+        return (
+            f"grid_dims: {self.grid_dims}, feature_dims: {self._num_features}, voxel_size: {self._voxel_size}, "
+            f"grid_location: {self._grid_location}, tunable: {self._tunable}"
+        )
+
+    def get_bounding_volume_vertices(self) -> Tensor:
+        (x0, x1), (y0, y1), (z0, z1) = self._aabb
+        return torch.tensor([[x, y, z] for x in (x0, x1) for y in (y0, y1) for z in (z0, z1)], dtype=torch.float32)
+
+    def test_inside_volume(self, points: Tensor) -> Tensor:
+        """strict ``lo < p < hi`` on all three axes -> bool ``[..., 1]``"""
+        inside = None
+        for axis, (lo, hi) in enumerate(self._aabb):
+            coord = points[..., axis : axis + 1]
+            test = torch.logical_and(coord > lo, coord < hi)
+            inside = test if inside is None else torch.logical_and(inside, test)
+        return inside
+
+    # ------------------------------------------------------------------ kernels
+    def kernel_desc(self, densities: Optional[Tensor] = None, features: Optional[Tensor] = None) -> _kernels.GridDesc:
+        """Descriptor handed to the C ABI (pointers + the fp32 constants of the point -> grid map)."""
+        if not (_is_identity(self._feature_preactivation) and _is_identity(self._feature_postactivation)):
+            raise NotImplementedError("feature pre-/post-activations other than Identity are not supported by the fused B200 kernels")
+        pre_id, post_id = classify_density_activations(self._density_preactivation, self._density_postactivation)
+        coeffs = [range_map_coefficients(axis_range, (-1.0, 1.0)) for axis_range in self._aabb]
+        return _kernels.GridDesc(
+            densities=self._densities.detach() if densities is None else densities.detach(),
+            features=self._features.detach() if features is None else features.detach(),
+            num_features=self._num_features,
+            aabb=tuple(self._aabb),
+            norm_scale=[float(s) for s, _ in coeffs],
+            norm_bias=[float(b) for _, b in coeffs],
+            density_scale=float(self._expected_density_scale),
+            density_pre=pre_id,
+            density_post=post_id,
+        )
+
+    def forward(self, points: Tensor, viewdirs: Optional[Tensor] = None) -> Tensor:
+        """Trilinearly interpolated ``[N, F + 1]`` = (features..., activated density) at ``points [N, 3]``.
+
+        With a ``radiance_transfer_function`` and ``viewdirs`` the features are mapped through it first
+        (``[N, 3 + 1]``), as in the reference.
+        """
+        values = _GridLookup.apply(self._densities, self._features, points, self)
+        if self._radiance_transfer_function is not None and viewdirs is not None:
+            radiance = self._radiance_transfer_function(values[..., :-1], viewdirs)
+            values = torch.cat([radiance, values[..., -1:]], dim=-1)
+        return values
+
+
+def scale_voxel_grid_with_required_output_size(voxel_grid: VoxelGrid, output_size: Tuple[int, int, int], mode: str = "trilinear") -> VoxelGrid:
+    """Resample a grid to ``output_size`` voxels (3x per training run: host-side PyTorch, not a hot path)."""
+    unified = torch.cat([voxel_grid.features, voxel_grid.densities], dim=-1)
+    resized = interpolate(
+        unified.permute(3, 0, 1, 2)[None, ...], size=output_size, mode=mode, align_corners=False, recompute_scale_factor=False
+    )[0].permute(1, 2, 3, 0)
+    assert tuple(resized.shape[:-1]) == tuple(output_size)
+    old = voxel_grid.voxel_size
+    new_voxel_size = VoxelSize(
+        (old.x_size * voxel_grid.width_x) / output_size[0],
+        (old.y_size * voxel_grid.depth_y) / output_size[1],
+        (old.z_size * voxel_grid.height_z) / output_size[2],
+    )
+    return VoxelGrid(
+        densities=resized[..., -1:].contiguous(),
+        features=resized[..., :-1],
+        voxel_size=new_voxel_size,
+        **voxel_grid.get_config_dict(),
+    )
+
+
+def create_voxel_grid_from_saved_info_dict(saved_info: Dict[str, Any]) -> VoxelGrid:
+    state = saved_info[THRE3D_REPR][STATE_DICT]
+    voxel_grid = VoxelGrid(
+        densities=torch.empty_like(state[u_DENSITIES]),
+        features=torch.empty_like(state[u_FEATURES]),
+        **saved_info[THRE3D_REPR][CONFIG_DICT],
+    )
+    voxel_grid.load_state_dict(state)
+    return voxel_grid
