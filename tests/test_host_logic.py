@@ -1,0 +1,325 @@
+"""Host-side mirror of the reference interface, on CPU tensors (no kernels run here): VoxelGrid storage and
+state-dict contract, config handling, VolumetricModel bookkeeping / checkpoints, camera helpers, ray glue,
+the loud refusal to render on CPU, and the 2-process (gloo) gradient all-reduce plumbing."""
+import dataclasses
+import os
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+from thr3ed_atom_b200 import _abi
+from thr3ed_atom_b200.modules.volumetric_model import VolumetricModel, create_volumetric_model_from_saved_model
+from thr3ed_atom_b200.rendering.volumetric.accumulate import density2occupancy_pb
+from thr3ed_atom_b200.rendering.volumetric.render_interface import Rays, RenderOut, render
+from thr3ed_atom_b200.rendering.volumetric.utils.misc import (
+    collate_rays,
+    collate_rendered_output,
+    compute_expected_density_scale_for_relu_field_grid,
+    flatten_rays,
+    reshape_rendered_output,
+    sample_random_rays_and_pixels_synchronously,
+)
+from thr3ed_atom_b200.thre3d_reprs.renderers import SHVoxGridRenderConfig, make_render_args, render_hints, render_sh_voxel_grid
+from thr3ed_atom_b200.thre3d_reprs.voxels import (
+    VoxelGrid,
+    VoxelGridLocation,
+    VoxelSize,
+    classify_density_activations,
+    create_voxel_grid_from_saved_info_dict,
+    padded_feature_stride,
+    scale_voxel_grid_with_required_output_size,
+)
+from thr3ed_atom_b200.utils.imaging_utils import (
+    CameraBounds,
+    CameraIntrinsics,
+    adjust_dynamic_range,
+    get_thre360_animation_poses,
+    get_thre360_spiral_animation_poses,
+    pose_spherical,
+    range_map_coefficients,
+    scale_camera_intrinsics,
+)
+
+
+def _grid(deg=2, dims=(4, 5, 6), tunable=True, **kw):
+    g = torch.Generator().manual_seed(0)
+    nf = 3 * (deg + 1) ** 2
+    return VoxelGrid(
+        densities=torch.rand((*dims, 1), generator=g),
+        features=torch.rand((*dims, nf), generator=g),
+        voxel_size=VoxelSize(0.5, 0.4, 0.3),
+        grid_location=VoxelGridLocation(0.1, -0.2, 0.3),
+        density_preactivation=torch.nn.Identity(),
+        density_postactivation=torch.nn.ReLU(),
+        expected_density_scale=33.0,
+        tunable=tunable,
+        **kw,
+    )
+
+
+# ---------------------------------------------------------------------------- VoxelGrid
+@pytest.mark.parametrize("deg,stride", [(0, 4), (1, 12), (2, 28), (3, 48)])
+def test_feature_storage_is_padded_to_whole_16_byte_vectors(deg, stride):
+    grid = _grid(deg)
+    nf = 3 * (deg + 1) ** 2
+    assert padded_feature_stride(nf) == stride
+    assert tuple(grid.feature_storage.shape) == (4, 5, 6, stride) and grid.feature_storage.is_contiguous()
+    assert tuple(grid.features.shape) == (4, 5, 6, nf)
+    assert tuple(grid.densities.shape) == (4, 5, 6, 1)
+    assert grid.grid_dims == (4, 5, 6) and (grid.width_x, grid.depth_y, grid.height_z) == (4, 5, 6)
+    # parameters are the leaves Adam sees (reference trainers.py:238-245): densities + (padded) features
+    assert [tuple(p.shape) for p in grid.parameters()] == [(4, 5, 6, 1), (4, 5, 6, stride)]
+    # in-place initialisation through the getters (reference trainers.py:151-152) writes through the view
+    with torch.no_grad():
+        torch.nn.init.uniform_(grid.features, 2.0, 3.0)
+        torch.nn.init.uniform_(grid.densities, -1.0, 1.0)
+    assert float(grid.feature_storage[..., :nf].min()) >= 2.0
+    if stride != nf:
+        assert not bool(grid.feature_storage[..., nf:].any())
+
+
+def test_state_dict_uses_the_reference_keys_and_shapes_and_round_trips():
+    grid = _grid(2)
+    sd = grid.state_dict()
+    assert list(sd.keys()) == ["_densities", "_features"]  # reference thre3d_reprs/constants.py:10-11
+    assert tuple(sd["_features"].shape) == (4, 5, 6, 27) and tuple(sd["_densities"].shape) == (4, 5, 6, 1)
+    assert torch.equal(sd["_features"], grid.features.detach())
+    other = _grid(2)
+    with torch.no_grad():
+        other.features.zero_()
+    other.load_state_dict(sd)
+    assert torch.equal(other.features, grid.features) and torch.equal(other.densities, grid.densities)
+    assert not bool(other.feature_storage[..., 27:].any())
+    # non-tunable grids keep plain tensors (not parameters / not in the state dict), as in the reference
+    frozen = _grid(2, tunable=False)
+    assert list(frozen.parameters()) == [] and list(frozen.state_dict().keys()) == []
+
+
+def test_setters_check_shapes_and_rewrap_parameters():
+    grid = _grid(2)
+    new_f = torch.ones(4, 5, 6, 27)
+    grid.features = new_f
+    assert isinstance(grid.feature_storage, torch.nn.Parameter) and torch.equal(grid.features, new_f)
+    grid.densities = torch.full((4, 5, 6, 1), 2.0)
+    assert isinstance(grid.densities, torch.nn.Parameter) and float(grid.densities.mean()) == 2.0
+    with pytest.raises(AssertionError):
+        grid.features = torch.ones(4, 5, 6, 12)
+    with pytest.raises(AssertionError):
+        grid.densities = torch.ones(4, 5, 7, 1)
+    with pytest.raises(AssertionError):
+        VoxelGrid(torch.zeros(2, 2, 2), torch.zeros(2, 2, 2, 3), VoxelSize())
+
+
+def test_aabb_config_dicts_and_kernel_descriptor():
+    grid = _grid(2)
+    aabb = grid.aabb
+    assert aabb.x_range == pytest.approx((0.1 - 1.0, 0.1 + 1.0)) and aabb.y_range == pytest.approx((-1.2, 0.8))
+    assert aabb.z_range == pytest.approx((0.3 - 0.9, 0.3 + 0.9))
+    verts = grid.get_bounding_volume_vertices()
+    assert tuple(verts.shape) == (8, 3) and float(verts[:, 0].min()) == pytest.approx(-0.9)
+    cfg = grid.get_config_dict()
+    assert set(cfg) == {"grid_location", "density_preactivation", "density_postactivation", "feature_preactivation",
+                        "feature_postactivation", "radiance_transfer_function", "expected_density_scale", "tunable"}
+    assert set(grid.get_save_config_dict()) == set(cfg) | {"voxel_size"}
+    inside = grid.test_inside_volume(torch.tensor([[0.1, -0.2, 0.3], [-0.9, 0.0, 0.0], [5.0, 0.0, 0.0]]))
+    assert inside.squeeze(-1).tolist() == [True, False, False]  # strict inequalities: a point ON the plane is outside
+    desc = grid.kernel_desc()
+    assert (desc.density_pre, desc.density_post) == (_abi.PRE_IDENTITY, _abi.POST_RELU)
+    s, b = range_map_coefficients(aabb.x_range, (-1.0, 1.0))
+    assert desc.norm_scale[0] == float(s) and desc.norm_bias[0] == float(b)
+    # the voxel_size setter does not move the bounding box (reference voxels.py:166-168)
+    grid.voxel_size = VoxelSize(1.0, 1.0, 1.0)
+    assert grid.aabb == aabb and grid.voxel_size == VoxelSize(1.0, 1.0, 1.0)
+    assert "grid_dims: (4, 5, 6)" in repr(grid)
+
+
+def test_activation_classification():
+    assert classify_density_activations(torch.nn.Identity(), torch.nn.ReLU()) == (_abi.PRE_IDENTITY, _abi.POST_RELU)
+    assert classify_density_activations(torch.nn.Identity(), torch.nn.Softplus()) == (_abi.PRE_IDENTITY, _abi.POST_SOFTPLUS)
+    assert classify_density_activations(torch.abs, torch.nn.Identity()) == (_abi.PRE_ABS, _abi.POST_IDENTITY)
+    with pytest.raises(NotImplementedError):
+        classify_density_activations(torch.exp, torch.nn.Identity())
+    with pytest.raises(NotImplementedError):
+        classify_density_activations(torch.nn.Identity(), torch.nn.Softplus(beta=2.0))
+    with pytest.raises(NotImplementedError):
+        _grid(2, feature_postactivation=torch.nn.Sigmoid()).kernel_desc()
+
+
+def test_rescaling_a_grid_matches_trilinear_interpolate():
+    grid = _grid(1, dims=(4, 4, 4))
+    bigger = scale_voxel_grid_with_required_output_size(grid, (8, 6, 5))
+    assert bigger.grid_dims == (8, 6, 5) and isinstance(bigger.densities, torch.nn.Parameter)
+    assert bigger.voxel_size == pytest.approx((0.5 * 4 / 8, 0.4 * 4 / 6, 0.3 * 4 / 5))
+    both = torch.cat([grid.features, grid.densities], -1).permute(3, 0, 1, 2)[None]
+    want = torch.nn.functional.interpolate(both, size=(8, 6, 5), mode="trilinear", align_corners=False)[0].permute(1, 2, 3, 0)
+    assert torch.allclose(bigger.features, want[..., :-1]) and torch.allclose(bigger.densities, want[..., -1:])
+    assert bigger.aabb.x_range == pytest.approx(grid.aabb.x_range)
+
+
+# ---------------------------------------------------------------------------- config / model facade
+def test_render_config_has_the_reference_fields_in_order():
+    names = [f.name for f in dataclasses.fields(SHVoxGridRenderConfig)]
+    assert names == ["num_samples_per_ray", "camera_bounds", "perturb_sampled_points", "optimized_sampling", "density2occupancy",
+                     "radiance_hdr_tone_map", "stochastic_density_noise_std", "white_bkgd", "render_diffuse",
+                     "render_num_samples_per_ray", "parallel_rays_chunk_size"]  # reference renderers.py:28-45
+    cfg = SHVoxGridRenderConfig(64, CameraBounds(1.0, 2.0))
+    assert (cfg.perturb_sampled_points, cfg.optimized_sampling, cfg.white_bkgd, cfg.render_diffuse) == (True, False, False, False)
+    assert cfg.density2occupancy is density2occupancy_pb and cfg.radiance_hdr_tone_map is torch.sigmoid
+    assert (cfg.stochastic_density_noise_std, cfg.render_num_samples_per_ray, cfg.parallel_rays_chunk_size) == (0.0, 1024, 32768)
+    with render_hints(image_hw=(2, 3), rng_seed=5):
+        args = make_render_args(cfg)
+    assert args.perturb and args.rng_seed == 5 and args.image_hw == (2, 3) and args.flags() == _abi.FLAG_PERTURB
+    torch.manual_seed(3)
+    a = make_render_args(cfg).rng_seed
+    torch.manual_seed(3)
+    assert make_render_args(cfg).rng_seed == a  # default seed follows torch.manual_seed
+    flags = make_render_args(dataclasses.replace(cfg, perturb_sampled_points=False, white_bkgd=True, render_diffuse=True, optimized_sampling=True)).flags()
+    assert flags == _abi.FLAG_WHITE_BKGD | _abi.FLAG_DIFFUSE | _abi.FLAG_OPTIMIZED_SAMPLING
+    assert float(density2occupancy_pb(torch.tensor(2.0), torch.tensor(0.5))) == pytest.approx(1 - np.exp(-1.0))
+
+
+def test_volumetric_model_bookkeeping_and_checkpoint_round_trip(tmp_path):
+    grid = _grid(2)
+    cfg = SHVoxGridRenderConfig(32, CameraBounds(1.8, 6.6), white_bkgd=True)
+    vol_mod = VolumetricModel(grid, render_sh_voxel_grid, cfg, device=torch.device("cpu"))
+    assert vol_mod.render_procedure is render_sh_voxel_grid and vol_mod.thre3d_repr is grid and vol_mod.render_config is cfg
+    updated = VolumetricModel._update_render_config(cfg, {"render_diffuse": True, "num_samples_per_ray": 8})
+    assert updated.render_diffuse and updated.num_samples_per_ray == 8 and not cfg.render_diffuse  # original untouched
+    with pytest.raises(ValueError, match="Unknown render configuration field"):
+        VolumetricModel._update_render_config(cfg, {"nope": 1})
+    info = vol_mod.get_save_info(extra_info={"camera_bounds": CameraBounds(1.8, 6.6), "hemispherical_radius": 4.03})
+    assert set(info) == {"thre3d_repr", "render_procedure", "render_config_type", "render_config", "extra_info"}
+    assert info["render_procedure"] is render_sh_voxel_grid and info["render_config_type"] is SHVoxGridRenderConfig
+    path = tmp_path / "model.pth"
+    torch.save(info, path)
+    loaded, extra = create_volumetric_model_from_saved_model(path, create_voxel_grid_from_saved_info_dict, device=torch.device("cpu"))
+    assert extra["hemispherical_radius"] == 4.03 and loaded.render_config == cfg
+    assert torch.equal(loaded.thre3d_repr.features, grid.features) and torch.equal(loaded.thre3d_repr.densities, grid.densities)
+    assert loaded.thre3d_repr.voxel_size == grid.voxel_size and loaded.render_procedure is render_sh_voxel_grid
+    # the procedure and config are pickled by qualified name
+    assert pickle.loads(pickle.dumps(render_sh_voxel_grid)) is render_sh_voxel_grid
+
+
+def test_rendering_cpu_tensors_is_refused_not_emulated():
+    grid = _grid(2)
+    rays = Rays(torch.zeros(5, 3), torch.ones(5, 3))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        render_sh_voxel_grid(grid, rays, SHVoxGridRenderConfig(8, CameraBounds(1.0, 2.0)))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        grid(torch.zeros(4, 3))
+    with pytest.raises(AssertionError, match="FLAT RAYS"):
+        render_sh_voxel_grid(grid, Rays(torch.zeros(2, 2, 3), torch.ones(2, 2, 3)), SHVoxGridRenderConfig(8, CameraBounds(1.0, 2.0)))
+
+
+# ---------------------------------------------------------------------------- ray / output glue, cameras
+def test_ray_and_output_containers():
+    rays = Rays(torch.arange(24.0).reshape(2, 4, 3), torch.ones(2, 4, 3))
+    flat = flatten_rays(rays)
+    assert len(flat) == 8 and tuple(flat[2:5].origins.shape) == (3, 3)
+    both = collate_rays([flat, flat])
+    assert len(both) == 16
+    with pytest.raises(AssertionError):
+        Rays(torch.zeros(3, 3), torch.zeros(4, 3))
+    pix = torch.arange(16.0)[:, None].repeat(1, 3)
+    sub_rays, sub_pix = sample_random_rays_and_pixels_synchronously(both, pix, 5)
+    assert len(sub_rays) == 5 and tuple(sub_pix.shape) == (5, 3)
+    idx = sub_pix[:, 0].long()
+    assert torch.equal(sub_rays.origins, both.origins[idx])  # rays and pixels stay in sync
+    out = RenderOut(torch.zeros(8, 3), torch.zeros(8, 1), {"disparity": torch.ones(8, 1)})
+    merged = collate_rendered_output([out, out])
+    assert tuple(merged.colour.shape) == (16, 3) and tuple(merged.extra["disparity"].shape) == (16, 1)
+    img = reshape_rendered_output(merged, CameraIntrinsics(4, 4, 10.0))
+    assert tuple(img.colour.shape) == (4, 4, 3) and tuple(img.extra["disparity"].shape) == (4, 4, 1)
+    assert RenderOut(torch.zeros(1, 3), torch.zeros(1, 1)).extra == {}
+    with pytest.raises(AssertionError):
+        RenderOut(torch.zeros(2, 4), torch.zeros(2, 1))
+    # the generic 3-stage driver still composes user stages
+    res = render(flat, CameraBounds(0, 1), 2, lambda r, b, n: ("s", n), lambda s, r: ("p", s), lambda p, r: RenderOut(torch.zeros(8, 3), torch.zeros(8, 1)))
+    assert isinstance(res, RenderOut)
+    assert compute_expected_density_scale_for_relu_field_grid((3.0, 3.0, 3.0)) == pytest.approx(100.0 / 3.0)
+
+
+def test_camera_helpers():
+    from cases import spherical_pose
+
+    pose = pose_spherical(30.0, 60.0, 4.031128)
+    rot, trans = spherical_pose(30.0, 60.0, 4.031128)
+    np.testing.assert_allclose(pose.rotation.numpy(), rot, atol=1e-7)
+    np.testing.assert_allclose(pose.translation.numpy(), trans, atol=1e-6)
+    assert float(torch.linalg.norm(pose.translation)) == pytest.approx(4.031128, rel=1e-6)
+    assert scale_camera_intrinsics(CameraIntrinsics(800, 800, 1111.11), 0.5) == CameraIntrinsics(400, 400, 555.555)
+    assert len(get_thre360_animation_poses(4.0, 60.0, 9)) == 8
+    assert len(get_thre360_spiral_animation_poses((1.0, 3.0), 2.0, 2, 11)) == 10
+    x = np.array([0.0, 5.0, 10.0], np.float32)
+    np.testing.assert_allclose(adjust_dynamic_range(x, (0, 10), (-1, 1), slack=True), [-1, 0, 1], atol=1e-6)
+    np.testing.assert_allclose(adjust_dynamic_range(x, (0, 5), (0, 1)), [0, 1, 1], atol=1e-6)  # slack=False clips
+
+
+# ---------------------------------------------------------------------------- 2-process data parallelism (gloo)
+def _dp_worker(rank, world, port, tmp):
+    import torch.distributed as dist
+
+    from helpers import CASES, build_inputs
+    from oracle import torch_port as tp
+    from thr3ed_atom_b200.distributed import all_reduce_grid_gradients, broadcast_grid, shard_rays, shard_views
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        case = CASES["deg2_16cube"]
+        inp = build_inputs(case)
+        n = 301  # not divisible by the world size
+        o, d = torch.from_numpy(inp["origins"][:n]), torch.from_numpy(inp["directions"][:n])
+        pixels = torch.from_numpy(np.random.RandomState(0).uniform(size=(n, 3)).astype(np.float32))
+        grid = VoxelGrid(torch.from_numpy(inp["densities"]) + rank, torch.from_numpy(inp["features"]) + rank, VoxelSize(*case.voxel_size),
+                         density_preactivation=torch.nn.Identity(), density_postactivation=torch.nn.ReLU(),
+                         expected_density_scale=case.density_scale, tunable=True)
+        broadcast_grid(grid, src=0)  # replicas must start identical
+        shard = shard_rays(Rays(o, d), pixels)
+        assert shard.end - shard.start in (150, 151) and shard.total == n
+        assert shard_views(8) == ([0, 1, 2, 3] if rank == 0 else [4, 5, 6, 7])
+
+        def oracle_loss(dens, feat, rays_o, rays_d, px):  # stand-in renderer for the CPU test: the oracle (test infra)
+            og = tp.OracleGrid(dens, feat, case.voxel_size, case.location, case.density_scale, "identity", "relu")
+            out = tp.render(og, rays_o, rays_d, num_samples=16, near=case.near, far=case.far, white_bkgd=True)
+            return torch.nn.functional.l1_loss(out["colour"], px)
+
+        loss = oracle_loss(grid.densities, grid.features, shard.rays.origins, shard.rays.directions, shard.pixels) * shard.loss_weight
+        loss.backward()
+        all_reduce_grid_gradients(grid)
+        # single-process reference: the mean over ALL rays
+        dens = torch.from_numpy(inp["densities"]).requires_grad_(True)
+        feat = torch.from_numpy(inp["features"]).requires_grad_(True)
+        oracle_loss(dens, feat, o, d, pixels).backward()
+        assert torch.allclose(grid.densities.grad, dens.grad, atol=1e-7, rtol=1e-5)
+        assert torch.allclose(grid.feature_storage.grad[..., :27], feat.grad, atol=1e-7, rtol=1e-5)
+        assert not bool(grid.feature_storage.grad[..., 27:].any())
+        torch.save(torch.tensor(1), os.path.join(tmp, f"ok{rank}"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_process_ray_sharding_and_gradient_all_reduce(tmp_path):
+    import socket
+
+    import torch.multiprocessing as mp
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_dp_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+
+
+def test_shard_bounds_cover_everything_once():
+    from thr3ed_atom_b200.distributed import shard_bounds
+
+    for n in (0, 1, 7, 640000):
+        for w in (1, 2, 3, 8):
+            spans = [shard_bounds(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [e - s for s, e in spans]
+            assert max(sizes) - min(sizes) <= 1
