@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define R3D_ABI_VERSION 1
+#define R3D_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define R3D_API __attribute__((visibility("default")))
@@ -112,6 +112,10 @@ typedef struct R3dRenderOut {
   float* depth;      /* [N]    (== [N][1]) */
   float* acc;        /* [N]    accumulated_weight */
   float* disparity;  /* [N]    may be NULL */
+  float* sample_cache; /* optional [S][N][4] fp32, 16-byte aligned.  Forward: when non-NULL, (sigmoid(raw) rgb, sigma) of every
+                          sample with sigma != 0 is stored at [sample][ray] (other entries are left untouched).  Backward
+                          (`saved`): when non-NULL the per-sample radiance is read back instead of being re-gathered from
+                          the grid.  Trades 16*N*S bytes of HBM for the second 8-corner gather. */
 } R3dRenderOut;
 
 /* upstream gradients dL/d(output); any pointer may be NULL (= zero). */

@@ -152,29 +152,38 @@ def test_point_lookup_matches_reference(name, cuda_device):
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["deg2_16cube", "c1_32cube_deg0"])
 def test_unpadded_reference_layout_gives_the_same_result(name, cuda_device):
+    """The C ABI accepts any record stride: whole 32-byte sectors (256-bit loads, what VoxelGrid stores), whole 16-byte
+    vectors (128-bit loads) and the reference's unpadded layout (scalar loads).  All three give the same result."""
     from thr3ed_atom_b200 import _kernels
     from thr3ed_atom_b200.thre3d_reprs.renderers import make_render_args
 
     case = CASES[name]
     inp = build_inputs(case)
     grid = make_cuda_grid(case, inp, cuda_device)
+    nf = inp["features"].shape[-1]
     padded = grid.kernel_desc()
     unpadded = dataclasses.replace(padded, features=torch.from_numpy(inp["features"]).to(cuda_device).contiguous())
+    stride4 = (nf + 3) // 4 * 4
+    vec4 = torch.zeros((*inp["features"].shape[:3], stride4), device=cuda_device)
+    vec4[..., :nf] = unpadded.features
+    vec4 = dataclasses.replace(padded, features=vec4)
     assert padded.features.shape[-1] % 4 == 0 and unpadded.features.shape[-1] % 4 != 0
     args = make_render_args(make_cuda_config(case))
     o, d = torch.from_numpy(inp["origins"]).to(cuda_device), torch.from_numpy(inp["directions"]).to(cuda_device)
-    out_p = _kernels.render_forward(padded, o, d, args)
-    out_u = _kernels.render_forward(unpadded, o, d, args)
-    for a, b in zip(out_p[:3], out_u[:3]):
-        assert torch.equal(a, b)
     gc = torch.from_numpy(inp["grad_colour"]).to(cuda_device)
-    gp_d, gp_f = torch.zeros_like(padded.densities), torch.zeros_like(padded.features)
-    gu_d, gu_f = torch.zeros_like(unpadded.densities), torch.zeros_like(unpadded.features)
-    _kernels.render_backward(padded, o, d, args, out_p[:3], (gc, None, None, None), gp_d, gp_f)
-    _kernels.render_backward(unpadded, o, d, args, out_u[:3], (gc, None, None, None), gu_d, gu_f)
-    nf = inp["features"].shape[-1]
-    assert rel_l2(gp_f[..., :nf].cpu().numpy(), gu_f.cpu().numpy()) < 1e-5
-    assert rel_l2(gp_d.cpu().numpy(), gu_d.cpu().numpy()) < 1e-5
+    results = []
+    for desc in (padded, vec4, unpadded):
+        out = _kernels.render_forward(desc, o, d, args)
+        g_d, g_f = torch.zeros_like(desc.densities), torch.zeros_like(desc.features)
+        _kernels.render_backward(desc, o, d, args, out[:3], (gc, None, None, None), g_d, g_f)
+        results.append((out, g_d, g_f))
+    (out_p, gp_d, gp_f) = results[0]
+    for out_o, go_d, go_f in results[1:]:
+        for a, b in zip(out_p[:3], out_o[:3]):
+            assert torch.equal(a, b)
+        assert rel_l2(gp_f[..., :nf].cpu().numpy(), go_f[..., :nf].cpu().numpy()) < 1e-5
+        assert rel_l2(gp_d.cpu().numpy(), go_d.cpu().numpy()) < 1e-5
+        assert not bool(go_f[..., nf:].any())
 
 
 # ---------------------------------------------------------------------------------------------
@@ -415,7 +424,7 @@ def test_config3_shape_properties(cuda_device):
     assert float(acc.min()) >= 0.0 and float(acc.max()) <= 1.0 + 1e-5
     assert float(out.colour.min()) >= -1e-6 and float(out.colour.max()) <= 1.0 + 1e-5
     assert not bool(torch.isnan(out.colour).any()) and not bool(torch.isnan(gf1).any())
-    assert not bool(gf1[..., 27].any()), "padding lane received gradient"
+    assert not bool(gf1[..., 27:].any()), "padding lanes received gradient"
 
     # batch-split invariance
     half = n // 2

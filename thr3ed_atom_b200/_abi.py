@@ -11,7 +11,7 @@ from pathlib import Path
 from typing import Optional
 
 LIB_PATH = Path(__file__).resolve().parent / "_lib" / "libr3d_b200.so"
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # enums of r3d_b200.h
 PRE_IDENTITY, PRE_ABS = 0, 1
@@ -74,7 +74,7 @@ class R3dRenderConfig(C.Structure):
 
 
 class R3dRenderOut(C.Structure):
-    _fields_ = [("colour", C.c_void_p), ("depth", C.c_void_p), ("acc", C.c_void_p), ("disparity", C.c_void_p)]
+    _fields_ = [("colour", C.c_void_p), ("depth", C.c_void_p), ("acc", C.c_void_p), ("disparity", C.c_void_p), ("sample_cache", C.c_void_p)]
 
 
 class R3dRenderOutGrad(C.Structure):

@@ -142,8 +142,19 @@ def _pack_call(grid: GridDesc, origins: Optional[Tensor], directions: Optional[T
     return g, r, c, keep
 
 
-def render_forward(grid: GridDesc, origins: Optional[Tensor], directions: Optional[Tensor], args: RenderArgs):
-    """Fused forward render.  Returns ``(colour [N,3], depth [N,1], acc [N,1], disparity [N,1])``."""
+def sample_cache_bytes(num_rays: int, num_samples: int) -> int:
+    return 16 * num_rays * num_samples
+
+
+def new_sample_cache(num_rays: int, num_samples: int, device) -> Tensor:
+    """Uninitialised ``[S, N, 4]`` buffer for the forward's per-sample (sigmoid(raw) rgb, sigma) records."""
+    return torch.empty((num_samples, num_rays, 4), dtype=torch.float32, device=device)
+
+
+def render_forward(grid: GridDesc, origins: Optional[Tensor], directions: Optional[Tensor], args: RenderArgs,
+                   sample_cache: Optional[Tensor] = None):
+    """Fused forward render.  Returns ``(colour [N,3], depth [N,1], acc [N,1], disparity [N,1])``.
+    ``sample_cache`` (``new_sample_cache``) is filled for the backward pass when given."""
     device = grid.features.device
     n = origins.shape[0] if args.camera is None else int(args.camera[0]) * int(args.camera[1])
     colour = torch.empty((n, 3), dtype=torch.float32, device=device)
@@ -151,7 +162,11 @@ def render_forward(grid: GridDesc, origins: Optional[Tensor], directions: Option
     acc = torch.empty((n, 1), dtype=torch.float32, device=device)
     disparity = torch.empty((n, 1), dtype=torch.float32, device=device)
     g, r, c, keep = _pack_call(grid, origins, directions, n, args)
-    out = _abi.R3dRenderOut(colour.data_ptr(), depth.data_ptr(), acc.data_ptr(), disparity.data_ptr())
+    if sample_cache is not None:
+        _require_cuda(sample_cache, "sample_cache")
+        if tuple(sample_cache.shape) != (args.num_samples, n, 4) or not sample_cache.is_contiguous():
+            raise ValueError(f"sample_cache must be a contiguous [{args.num_samples}, {n}, 4] tensor")
+    out = _abi.R3dRenderOut(colour.data_ptr(), depth.data_ptr(), acc.data_ptr(), disparity.data_ptr(), _ptr(sample_cache))
     with torch.cuda.device(device):
         _abi.check(_abi.lib().r3d_render_fwd(C.byref(g), C.byref(r), C.byref(c), C.byref(out), _stream(device)), "r3d_render_fwd")
     del keep
@@ -167,13 +182,15 @@ def render_backward(
     grads: Tuple[Optional[Tensor], Optional[Tensor], Optional[Tensor], Optional[Tensor]],
     grad_densities: Optional[Tensor],
     grad_features: Optional[Tensor],
+    sample_cache: Optional[Tensor] = None,
 ) -> None:
-    """Fused backward: accumulates into ``grad_densities`` / ``grad_features`` (same layout as the grid)."""
+    """Fused backward: accumulates into ``grad_densities`` / ``grad_features`` (same layout as the grid).
+    ``sample_cache`` must be the buffer the matching forward call filled (else the radiance is re-gathered)."""
     device = grid.features.device
     colour, depth, acc = saved
     n = colour.shape[0]
     g, r, c, keep = _pack_call(grid, origins, directions, n, args)
-    sv = _abi.R3dRenderOut(colour.data_ptr(), depth.data_ptr(), acc.data_ptr(), None)
+    sv = _abi.R3dRenderOut(colour.data_ptr(), depth.data_ptr(), acc.data_ptr(), None, _ptr(sample_cache))
     gs = [None if t is None else _require_cuda(t.contiguous(), "grad_output") for t in grads]
     go = _abi.R3dRenderOutGrad(*[_ptr(t) for t in gs])
     for t, ref in ((grad_densities, grid.densities), (grad_features, grid.features)):

@@ -27,6 +27,7 @@ struct OutP {
   float* __restrict__ depth;
   float* __restrict__ acc;
   float* __restrict__ disparity;
+  float4* __restrict__ cache;  // optional [S][N] (sigmoid(raw) rgb, sigma) of every sigma != 0 sample, for the backward
 };
 
 struct BwdP {
@@ -39,6 +40,7 @@ struct BwdP {
   const float* __restrict__ g_disp;
   float* __restrict__ gdens;  // outputs (nullable)
   float* __restrict__ gfeat;
+  const float4* __restrict__ cache;  // optional sample cache written by the forward pass
 };
 
 struct RayCtx {
@@ -70,8 +72,14 @@ __device__ __forceinline__ void setup_ray(const GridP& g, const RaysP& rp, const
   sample_range(g, r, near, far, c.S, s.i_lo, s.i_hi);
 }
 
+__device__ __forceinline__ void ldg256(const float* __restrict__ p, float* v) {
+  asm("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+      : "l"(p));
+}
+
 // ---- per-corner SH record contraction (forward) -------------------------------------------------
-template <int DEG, bool VEC>
+template <int DEG, int VEC>
 __device__ __forceinline__ void corner_radiance(const float* __restrict__ rec, const float (&Y)[(DEG + 1) * (DEG + 1)],
                                                 bool diffuse, float w, float& r, float& g, float& b) {
   constexpr int K = (DEG + 1) * (DEG + 1);
@@ -83,11 +91,15 @@ __device__ __forceinline__ void corner_radiance(const float* __restrict__ rec, c
     b = fmaf(wy, __ldg(rec + 2 * K), b);
     return;
   }
-  constexpr int NV = (F + 3) / 4;
+  constexpr int NV = (F + 7) / 8 * 2;  // float4 slots, rounded so that both vector widths fit
   float v[NV * 4];
-  if constexpr (VEC) {
+  if constexpr (VEC == 8) {
+    // Blackwell 256-bit global load (LDG.E.256): one request per 32-byte sector of the record
 #pragma unroll
-    for (int j = 0; j < NV; ++j) {
+    for (int j = 0; j < (F + 7) / 8; ++j) ldg256(rec + 8 * j, &v[8 * j]);
+  } else if constexpr (VEC == 4) {
+#pragma unroll
+    for (int j = 0; j < (F + 3) / 4; ++j) {
       const float4 q = __ldg(reinterpret_cast<const float4*>(rec) + j);
       v[4 * j] = q.x, v[4 * j + 1] = q.y, v[4 * j + 2] = q.z, v[4 * j + 3] = q.w;
     }
@@ -105,7 +117,7 @@ __device__ __forceinline__ void corner_radiance(const float* __restrict__ rec, c
   r = fmaf(w, sr, r), g = fmaf(w, sg, g), b = fmaf(w, sb, b);
 }
 
-template <int DEG, bool VEC>
+template <int DEG, int VEC>
 __device__ __forceinline__ void gather_radiance(const GridP& g, const Cell& c, const float (&Y)[(DEG + 1) * (DEG + 1)],
                                                 bool diffuse, float& rr, float& rg, float& rb) {
   rr = rg = rb = 0.f;
@@ -129,7 +141,7 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 
 // ---- per-corner gradient scatter (backward) -----------------------------------------------------
 // d coeff[ch][k] = Y_k * d raw_ch (SH is linear), times the corner's trilinear weight.
-template <int DEG, bool VEC>
+template <int DEG, int VEC>
 __device__ __forceinline__ void corner_scatter(float* __restrict__ rec, const float (&Y)[(DEG + 1) * (DEG + 1)],
                                                bool diffuse, float w, const float (&draw)[3]) {
   constexpr int K = (DEG + 1) * (DEG + 1);
@@ -141,7 +153,7 @@ __device__ __forceinline__ void corner_scatter(float* __restrict__ rec, const fl
     atomicAdd(rec + 2 * K, wd[2] * Y[0]);
     return;
   }
-  if constexpr (VEC) {
+  if constexpr (VEC != 0) {
     constexpr int NV = (F + 3) / 4;
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
@@ -162,7 +174,7 @@ __device__ __forceinline__ void corner_scatter(float* __restrict__ rec, const fl
 // =================================================================================================
 // forward
 // =================================================================================================
-template <int DEG, bool VEC>
+template <int DEG, int VEC>
 __global__ void __launch_bounds__(128) render_fwd_kernel(const GridP g, const RaysP rp, const CfgP c, const OutP out) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long ray = thread_to_ray(rp, t);
@@ -198,9 +210,11 @@ __global__ void __launch_bounds__(128) render_fwd_kernel(const GridP g, const Ra
           const float w = alpha * T;
           float rr, rg, rb;
           gather_radiance<DEG, VEC>(g, cell, Y, diffuse, rr, rg, rb);
-          cr = fmaf(w, sigmoidf_(rr), cr);
-          cg = fmaf(w, sigmoidf_(rg), cg);
-          cb = fmaf(w, sigmoidf_(rb), cb);
+          const float sr = sigmoidf_(rr), sg = sigmoidf_(rg), sb = sigmoidf_(rb);
+          if (out.cache) out.cache[(size_t)i * rp.n + ray] = make_float4(sr, sg, sb, sigma);
+          cr = fmaf(w, sr, cr);
+          cg = fmaf(w, sg, cg);
+          cb = fmaf(w, sb, cb);
           dep = fmaf(w, z, dep);
           acc += w;
           T *= (1.0f - alpha);
@@ -224,17 +238,15 @@ __global__ void __launch_bounds__(128) render_fwd_kernel(const GridP g, const Ra
   }
 }
 
-// =================================================================================================
-// backward
-// =================================================================================================
-template <int DEG, bool VEC>
-__global__ void __launch_bounds__(128) render_bwd_kernel(const GridP g, const RaysP rp, const CfgP c, const BwdP b) {
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long ray = thread_to_ray(rp, t);
-  if (ray < 0) return;
-
-  // ---- per-ray upstream gradients ----
-  float gc[3] = {0.f, 0.f, 0.f}, gd = 0.f, ga = 0.f;
+// Per-ray upstream gradients folded into the three numbers the march needs: g_c (3), g_d, g_a, plus
+// Total = sum_i w_i q_i rebuilt from the forward outputs.  Returns false when the ray receives no gradient.
+struct RayGrad {
+  float gc[3], gd, ga, total;
+};
+__device__ __forceinline__ bool load_ray_grad(const BwdP& b, const CfgP& c, long long ray, RayGrad& rg) {
+  float* gc = rg.gc;
+  gc[0] = gc[1] = gc[2] = 0.f;
+  float gd = 0.f, ga = 0.f;
   if (b.g_colour) gc[0] = __ldg(b.g_colour + 3 * ray), gc[1] = __ldg(b.g_colour + 3 * ray + 1), gc[2] = __ldg(b.g_colour + 3 * ray + 2);
   if (b.g_depth) gd = __ldg(b.g_depth + ray);
   if (b.g_acc) ga = __ldg(b.g_acc + ray);
@@ -259,8 +271,24 @@ __global__ void __launch_bounds__(128) render_bwd_kernel(const GridP g, const Ra
     cfr -= bg, cfg_ -= bg, cfb -= bg;
     ga -= (gc[0] + gc[1] + gc[2]);  // d(1 - acc)/d acc on every channel
   }
-  const float total = fmaf(gc[0], cfr, fmaf(gc[1], cfg_, fmaf(gc[2], cfb, fmaf(gd, dep_f, ga * acc_f))));
-  if (gc[0] == 0.f && gc[1] == 0.f && gc[2] == 0.f && gd == 0.f && ga == 0.f) return;
+  rg.gd = gd, rg.ga = ga;
+  rg.total = fmaf(gc[0], cfr, fmaf(gc[1], cfg_, fmaf(gc[2], cfb, fmaf(gd, dep_f, ga * acc_f))));
+  return !(gc[0] == 0.f && gc[1] == 0.f && gc[2] == 0.f && gd == 0.f && ga == 0.f);
+}
+
+// =================================================================================================
+// backward
+// =================================================================================================
+template <int DEG, int VEC>
+__global__ void __launch_bounds__(128) render_bwd_kernel(const GridP g, const RaysP rp, const CfgP c, const BwdP b) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long ray = thread_to_ray(rp, t);
+  if (ray < 0) return;
+
+  RayGrad rgd;
+  if (!load_ray_grad(b, c, ray, rgd)) return;
+  const float gc[3] = {rgd.gc[0], rgd.gc[1], rgd.gc[2]};
+  const float gd = rgd.gd, ga = rgd.ga, total = rgd.total;
 
   RayCtx s;
   float vx, vy, vz;
@@ -293,9 +321,15 @@ __global__ void __launch_bounds__(128) render_bwd_kernel(const GridP g, const Ra
         const float alpha = 1.0f - expf(-(sigma * delta));
         const float w = alpha * T;
         const float Tn = T * (1.0f - alpha);
-        float rr, rg, rb;
-        gather_radiance<DEG, VEC>(g, cell, Y, diffuse, rr, rg, rb);
-        const float sr = sigmoidf_(rr), sg = sigmoidf_(rg), sb = sigmoidf_(rb);
+        float sr, sg, sb;
+        if (b.cache && sigma != 0.0f) {
+          const float4 cv = __ldg(b.cache + (size_t)i * rp.n + ray);
+          sr = cv.x, sg = cv.y, sb = cv.z;
+        } else {
+          float rr, rg, rb;
+          gather_radiance<DEG, VEC>(g, cell, Y, diffuse, rr, rg, rb);
+          sr = sigmoidf_(rr), sg = sigmoidf_(rg), sb = sigmoidf_(rb);
+        }
         const float q = fmaf(gc[0], sr, fmaf(gc[1], sg, fmaf(gc[2], sb, fmaf(gd, z, ga))));
         prefix = fmaf(w, q, prefix);
         // sum_{j>i} w_j q_j = total - prefix.  It is empty for the last sample and once the transmittance is exactly 0.
@@ -341,6 +375,239 @@ __global__ void __launch_bounds__(128) render_bwd_kernel(const GridP g, const Ra
   }
 }
 
+
+// =================================================================================================
+// backward, warp-cooperative scatter (default)
+//
+// Profile of the thread-per-ray scatter above (profiles/r01_v0_ncu_full_summary.md): the L1 data pipe issues one
+// wavefront per distinct 128-byte line a request touches, and a 32-lane REDG.128 touches ~16 of them (each lane its
+// own voxel record); 56 such requests per marching step make the kernel L1/L2-reduction bound.  Here the scatter is
+// transposed through shared memory instead.  Per marching step of a warp (32 rays of an 8x4 pixel tile):
+//   1. every lane does the per-ray maths of its sample (position, cell, density, alpha, T, q, dL/dsigma, dL/draw); the
+//      per-sample sigmoid(raw)/sigma come from the forward's sample cache when there is one (no second gather),
+//   2. lanes publish their 8 corner weights, corner voxel offsets, dL/dsigma_pre and the product table
+//      P[e] = dL/draw[ch(e)] * Y[k(e)] (the SH part of the chain rule) in shared memory,
+//   3. lanes whose samples fall in the same interpolation cell are grouped (__match_any_sync); for every distinct
+//      cell the warp forms sum_members w[m][corner] * P[m][e] with LPR lanes per voxel record (one float4 each) and
+//      issues ONE 128-bit reduction per lane: a record is one coalesced, fully used line instead of 32 scattered
+//      lanes, and samples sharing a cell are summed before they reach L2.
+// =================================================================================================
+template <int DEG>
+struct CoopShape {
+  static constexpr int K = (DEG + 1) * (DEG + 1);
+  static constexpr int F = 3 * K;
+  static constexpr int NV = (F + 3) / 4;                              // float4s of a record that carry data
+  static constexpr int LPR = NV <= 1 ? 1 : (NV <= 4 ? 4 : (NV <= 8 ? 8 : 16));  // lanes per record
+  static constexpr int CPP = (32 / LPR) < 8 ? (32 / LPR) : 8;        // corners per pass
+  static constexpr int PASSES = 8 / CPP;
+  static constexpr int PROW = (NV % 2) ? 4 * NV : 4 * NV + 4;         // row stride: odd multiple of 4 floats => conflict-free
+  static constexpr int WROW = 12;                                     // 8 used; 12 keeps 128-bit stores conflict-free
+};
+
+template <int DEG>
+struct CoopSmem {
+  using S = CoopShape<DEG>;
+  float P[32 * S::PROW];
+  float W[32 * S::WROW];
+  int V[32 * S::WROW];
+  float D[32];
+};
+
+template <int DEG, int VEC>
+__global__ void __launch_bounds__(128) render_bwd_coop_kernel(const GridP g, const RaysP rp, const CfgP c, const BwdP b) {
+  using S = CoopShape<DEG>;
+  constexpr int K = S::K, F = S::F;
+  constexpr unsigned FULL = 0xffffffffu;
+  __shared__ __align__(16) CoopSmem<DEG> smem_all[4];
+  CoopSmem<DEG>& sm = smem_all[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
+
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long ray = thread_to_ray(rp, t);
+
+  // ---- per-ray state; lanes without work stay in the loop (the scatter is a warp-wide collective) ----
+  RayGrad rgd;
+  bool alive = (ray >= 0) && load_ray_grad(b, c, ray, rgd);
+  RayCtx s;
+  float Y[K];
+  float qmax = 0.f;
+  s.i_lo = 1, s.i_hi = 0;
+  if (alive) {
+    float vx, vy, vz;
+    setup_ray(g, rp, c, ray, s, vx, vy, vz);
+    sh_basis<DEG>(vx, vy, vz, Y);
+    qmax = fabsf(rgd.gc[0]) + fabsf(rgd.gc[1]) + fabsf(rgd.gc[2]) + fabsf(rgd.gd) * fmaxf(fabsf(s.dg.near), fabsf(s.dg.far)) + fabsf(rgd.ga);
+    alive = s.i_lo <= s.i_hi;
+  }
+  const bool diffuse = (c.flags & R3D_FLAG_DIFFUSE) != 0;
+  const float dmul = (g.pre == R3D_PRE_ABS) ? fabsf(g.dscale) : g.dscale;
+  const Ray& r = s.r;
+
+  // warp-uniform loop bounds
+  int lo = alive ? s.i_lo : 0x7fffffff, hi = alive ? s.i_hi : -1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = min(lo, __shfl_xor_sync(FULL, lo, o));
+    hi = max(hi, __shfl_xor_sync(FULL, hi, o));
+  }
+
+  // cooperative-phase role of this lane: float4 `cj` of corner `pass * CPP + cq`
+  const int cq = lane / S::LPR, cj = lane % S::LPR;
+  const bool role_ok = (cq < S::CPP) && (cj < S::NV);
+
+  float T = 1.0f, prefix = 0.f;
+  float z = 0.f;
+  bool have_z = false;
+  for (int i = lo; i <= hi; ++i) {
+    // ------------------------------------------------------------------ 1. per-lane sample maths
+    bool contributes = false;
+    float wc[8];
+    int vox[8];
+    float draw[3] = {0.f, 0.f, 0.f}, dpre = 0.f;
+    int key = -1;
+    if (alive && i >= s.i_lo && i <= s.i_hi) {
+      if (!have_z) z = s.dg.at(i), have_z = true;
+      const bool last = (i == c.S - 1);
+      const float zn = last ? 0.0f : s.dg.at(i + 1);
+      const float px = __fadd_rn(r.ox, __fmul_rn(r.dx, z));
+      const float py = __fadd_rn(r.oy, __fmul_rn(r.dy, z));
+      const float pz = __fadd_rn(r.oz, __fmul_rn(r.dz, z));
+      if (inside_aabb(g, px, py, pz)) {
+        Cell cell;
+        make_cell(g, px, py, pz, cell);
+        float dpost;
+        const float sigma = density_post(g.post, density_pre_interp(g, cell), dpost);
+        if (sigma != 0.0f || dpost != 0.0f) {
+          const float delta = last ? __fmul_rn(kInfinity, s.dnorm) : __fmul_rn(__fsub_rn(zn, z), s.dnorm);
+          const float alpha = 1.0f - expf(-(sigma * delta));
+          const float w = alpha * T;
+          const float Tn = T * (1.0f - alpha);
+          float sr, sg, sb;
+          if (b.cache && sigma != 0.0f) {  // written by the forward for exactly the sigma != 0 samples
+            const float4 cv = __ldg(b.cache + (size_t)i * rp.n + ray);
+            sr = cv.x, sg = cv.y, sb = cv.z;
+          } else {
+            float rr, rg, rb;
+            gather_radiance<DEG, VEC>(g, cell, Y, diffuse, rr, rg, rb);
+            sr = sigmoidf_(rr), sg = sigmoidf_(rg), sb = sigmoidf_(rb);
+          }
+          const float q = fmaf(rgd.gc[0], sr, fmaf(rgd.gc[1], sg, fmaf(rgd.gc[2], sb, fmaf(rgd.gd, z, rgd.ga))));
+          prefix = fmaf(w, q, prefix);
+          float suffix = 0.0f;  // see render_bwd_kernel for the clamp
+          if (!last && Tn != 0.0f) {
+            const float bound = Tn * qmax;
+            suffix = fminf(fmaxf(rgd.total - prefix, -bound), bound);
+          }
+          dpre = delta * (Tn * q - suffix) * dpost * dmul;
+          if (!b.gdens) dpre = 0.f;
+          if (b.gfeat) {
+            draw[0] = w * rgd.gc[0] * sr * (1.0f - sr);
+            draw[1] = w * rgd.gc[1] * sg * (1.0f - sg);
+            draw[2] = w * rgd.gc[2] * sb * (1.0f - sb);
+          }
+          contributes = (dpre != 0.f) || (draw[0] != 0.f) || (draw[1] != 0.f) || (draw[2] != 0.f);
+          if (contributes) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const int ix = k >> 2, iy = (k >> 1) & 1, iz = k & 1;
+              wc[k] = cell.wx[ix] * cell.wy[iy] * cell.wz[iz];
+              vox[k] = cell.ox[ix] + cell.oy[iy] + cell.oz[iz];
+            }
+            // the clamped offsets of the low corner identify the cell unless it is clamped at the border; fold the
+            // validity pattern in so that border cells with different zero-padding never merge
+            key = vox[0] ^ ((cell.wx[0] != 0.f) << 28) ^ ((cell.wy[0] != 0.f) << 29) ^ ((cell.wz[0] != 0.f) << 30);
+          }
+          T = Tn;
+          if (T == 0.0f) alive = false;  // every later weight is exactly 0
+        }
+      }
+      z = zn;
+    }
+    const unsigned act = __ballot_sync(FULL, contributes);
+    if (act == 0u) continue;
+
+    // ------------------------------------------------------------------ 2. publish
+    if (contributes) {
+      float* Prow = sm.P + lane * S::PROW;
+#pragma unroll
+      for (int j = 0; j < S::NV; ++j) {
+        float q4[4];
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+          const int e = 4 * j + l;
+          const bool on = (e < F) && (!(DEG > 0 && diffuse) || (e % K) == 0);
+          q4[l] = on ? draw[e / K] * Y[e % K] : 0.0f;
+        }
+        *reinterpret_cast<float4*>(Prow + 4 * j) = make_float4(q4[0], q4[1], q4[2], q4[3]);
+      }
+      float* Wrow = sm.W + lane * S::WROW;
+      *reinterpret_cast<float4*>(Wrow) = make_float4(wc[0], wc[1], wc[2], wc[3]);
+      *reinterpret_cast<float4*>(Wrow + 4) = make_float4(wc[4], wc[5], wc[6], wc[7]);
+      int* Vrow = sm.V + lane * S::WROW;
+      *reinterpret_cast<int4*>(Vrow) = make_int4(vox[0], vox[1], vox[2], vox[3]);
+      *reinterpret_cast<int4*>(Vrow + 4) = make_int4(vox[4], vox[5], vox[6], vox[7]);
+      sm.D[lane] = dpre;
+    }
+    // ------------------------------------------------------------------ 3. group by cell, cooperative reduction
+    __syncwarp();  // tables visible to the whole warp
+    unsigned peers = 0u;
+    if (contributes) peers = __match_any_sync(act, key);
+    const bool leader = contributes && ((int)(__ffs(peers) - 1) == lane);
+    unsigned leaders = __ballot_sync(FULL, leader);
+    while (leaders) {
+      const int L = __ffs(leaders) - 1;
+      leaders &= leaders - 1;
+      const unsigned members = __shfl_sync(FULL, peers, L);
+      if (b.gfeat) {
+#pragma unroll
+        for (int pass = 0; pass < S::PASSES; ++pass) {
+          const int corner = pass * S::CPP + cq;
+          if (role_ok) {
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            unsigned mm = members;
+            while (mm) {
+              const int m = __ffs(mm) - 1;
+              mm &= mm - 1;
+              const float wm = sm.W[m * S::WROW + corner];
+              const float4 p4 = *reinterpret_cast<const float4*>(sm.P + m * S::PROW + 4 * cj);
+              a.x = fmaf(wm, p4.x, a.x), a.y = fmaf(wm, p4.y, a.y), a.z = fmaf(wm, p4.z, a.z), a.w = fmaf(wm, p4.w, a.w);
+            }
+            if (a.x != 0.f || a.y != 0.f || a.z != 0.f || a.w != 0.f) {
+              float* dst = b.gfeat + (size_t)sm.V[L * S::WROW + corner] * (size_t)g.stride + 4 * cj;
+              if constexpr (VEC != 0) {
+                red_add_v4(dst, a.x, a.y, a.z, a.w);
+              } else {
+                if (4 * cj + 0 < F) atomicAdd(dst + 0, a.x);
+                if (4 * cj + 1 < F) atomicAdd(dst + 1, a.y);
+                if (4 * cj + 2 < F) atomicAdd(dst + 2, a.z);
+                if (4 * cj + 3 < F) atomicAdd(dst + 3, a.w);
+              }
+            }
+          }
+        }
+      }
+      if (b.gdens && lane < 8) {
+        float a = 0.f;
+        unsigned mm = members;
+        while (mm) {
+          const int m = __ffs(mm) - 1;
+          mm &= mm - 1;
+          a = fmaf(sm.W[m * S::WROW + lane], sm.D[m], a);
+        }
+        if (a != 0.f) {
+          const int vx_ = sm.V[L * S::WROW + lane];
+          if (g.pre == R3D_PRE_ABS) {
+            const float v = __ldg(g.dens + vx_);
+            a = (v > 0.f) ? a : ((v < 0.f) ? -a : 0.0f);  // d|x|/dx = sign(x), 0 at 0 (torch.abs)
+          }
+          atomicAdd(b.gdens + vx_, a);
+        }
+      }
+    }
+    __syncwarp();  // the tables are rewritten at the next contributing step
+  }
+}
+
 // =================================================================================================
 // measurement helper: mark voxels referenced as interpolation corners by in-volume samples
 // =================================================================================================
@@ -372,18 +639,41 @@ __global__ void __launch_bounds__(128) mark_touched_kernel(const GridP g, const 
 // host-side dispatch
 // =================================================================================================
 template <int DEG>
-static void launch_fwd(bool vec, dim3 grid, cudaStream_t st, const GridP& g, const RaysP& r, const CfgP& c, const OutP& o) {
-  if (vec)
-    render_fwd_kernel<DEG, true><<<grid, 128, 0, st>>>(g, r, c, o);
+static void launch_fwd(int vec, dim3 grid, cudaStream_t st, const GridP& g, const RaysP& r, const CfgP& c, const OutP& o) {
+  if (vec == 8)
+    render_fwd_kernel<DEG, 8><<<grid, 128, 0, st>>>(g, r, c, o);
+  else if (vec == 4)
+    render_fwd_kernel<DEG, 4><<<grid, 128, 0, st>>>(g, r, c, o);
   else
-    render_fwd_kernel<DEG, false><<<grid, 128, 0, st>>>(g, r, c, o);
+    render_fwd_kernel<DEG, 0><<<grid, 128, 0, st>>>(g, r, c, o);
 }
 template <int DEG>
-static void launch_bwd(bool vec, dim3 grid, cudaStream_t st, const GridP& g, const RaysP& r, const CfgP& c, const BwdP& b) {
-  if (vec)
-    render_bwd_kernel<DEG, true><<<grid, 128, 0, st>>>(g, r, c, b);
+static void launch_bwd(int vec, int variant, dim3 grid, cudaStream_t st, const GridP& g, const RaysP& r, const CfgP& c, const BwdP& b) {
+  if (variant & 1) {  // thread-per-ray scatter (kept for A/B measurement)
+    if (vec == 8)
+      render_bwd_kernel<DEG, 8><<<grid, 128, 0, st>>>(g, r, c, b);
+    else if (vec == 4)
+      render_bwd_kernel<DEG, 4><<<grid, 128, 0, st>>>(g, r, c, b);
+    else
+      render_bwd_kernel<DEG, 0><<<grid, 128, 0, st>>>(g, r, c, b);
+    return;
+  }
+  if (vec == 8)
+    render_bwd_coop_kernel<DEG, 8><<<grid, 128, 0, st>>>(g, r, c, b);
+  else if (vec == 4)
+    render_bwd_coop_kernel<DEG, 4><<<grid, 128, 0, st>>>(g, r, c, b);
   else
-    render_bwd_kernel<DEG, false><<<grid, 128, 0, st>>>(g, r, c, b);
+    render_bwd_coop_kernel<DEG, 0><<<grid, 128, 0, st>>>(g, r, c, b);
+}
+
+// widest vector access the feature layout allows: 8 floats (256-bit loads; records are whole 32-byte sectors),
+// 4 floats (128-bit) or scalar (the reference's unpadded layout)
+static int vector_width(const GridP& g, const void* grad_features) {
+  const auto aligned = [](const void* p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; };
+  const bool grad16 = grad_features == nullptr || aligned(grad_features, 16);
+  if (g.stride % 8 == 0 && aligned(g.feat, 32) && grad16) return 8;
+  if (g.stride % 4 == 0 && aligned(g.feat, 16) && grad16) return 4;
+  return 0;
 }
 
 static int grid_blocks(const RaysP& r, dim3& grid) {
@@ -407,10 +697,11 @@ extern "C" int r3d_render_fwd(const R3dGrid* grid, const R3dRays* rays, const R3
   if ((rc = to_device_params(grid, g)) || (rc = to_device_params(rays, r)) || (rc = to_device_params(cfg, r, c))) return rc;
   if (r.n == 0) return R3D_OK;
   if (!out || !out->colour || !out->depth || !out->acc) return fail(R3D_ERR_INVALID_ARGUMENT, "render output buffers are NULL");
-  OutP o{out->colour, out->depth, out->acc, out->disparity};
+  OutP o{out->colour, out->depth, out->acc, out->disparity, reinterpret_cast<float4*>(out->sample_cache)};
+  if (o.cache && !aligned16(o.cache)) return fail(R3D_ERR_INVALID_ARGUMENT, "sample_cache must be 16-byte aligned");
   dim3 blocks;
   if ((rc = grid_blocks(r, blocks))) return rc;
-  const bool vec = (g.stride % 4 == 0) && aligned16(g.feat);
+  const int vec = vector_width(g, nullptr);
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   switch (grid->sh_degree) {
     case 0: launch_fwd<0>(vec, blocks, st, g, r, c, o); break;
@@ -433,17 +724,19 @@ extern "C" int r3d_render_bwd(const R3dGrid* grid, const R3dRays* rays, const R3
     return fail(R3D_ERR_INVALID_ARGUMENT, "saved forward outputs (colour, depth, acc) are required by the backward pass");
   if (!grad_out || !grad_grid) return fail(R3D_ERR_INVALID_ARGUMENT, "grad_out / grad_grid is NULL");
   if (!grad_grid->densities && !grad_grid->features) return R3D_OK;
-  BwdP b{saved->colour,   saved->depth,       saved->acc,           grad_out->colour, grad_out->depth,
-         grad_out->acc,   grad_out->disparity, grad_grid->densities, grad_grid->features};
+  BwdP b{saved->colour,   saved->depth,        saved->acc,           grad_out->colour,     grad_out->depth,
+         grad_out->acc,   grad_out->disparity, grad_grid->densities, grad_grid->features,
+         reinterpret_cast<const float4*>(saved->sample_cache)};
+  if (b.cache && !aligned16(b.cache)) return fail(R3D_ERR_INVALID_ARGUMENT, "sample_cache must be 16-byte aligned");
   dim3 blocks;
   if ((rc = grid_blocks(r, blocks))) return rc;
-  const bool vec = (g.stride % 4 == 0) && aligned16(g.feat) && aligned16(b.gfeat);
+  const int vec = vector_width(g, b.gfeat);
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   switch (grid->sh_degree) {
-    case 0: launch_bwd<0>(vec, blocks, st, g, r, c, b); break;
-    case 1: launch_bwd<1>(vec, blocks, st, g, r, c, b); break;
-    case 2: launch_bwd<2>(vec, blocks, st, g, r, c, b); break;
-    default: launch_bwd<3>(vec, blocks, st, g, r, c, b); break;
+    case 0: launch_bwd<0>(vec, cfg->variant, blocks, st, g, r, c, b); break;
+    case 1: launch_bwd<1>(vec, cfg->variant, blocks, st, g, r, c, b); break;
+    case 2: launch_bwd<2>(vec, cfg->variant, blocks, st, g, r, c, b); break;
+    default: launch_bwd<3>(vec, cfg->variant, blocks, st, g, r, c, b); break;
   }
   return check_launch("r3d_render_bwd");
 }

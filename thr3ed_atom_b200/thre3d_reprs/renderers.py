@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import contextlib
 import dataclasses
+import os
 import threading
 from typing import Any, Callable, Optional, Tuple
 
@@ -89,8 +90,15 @@ class _FusedSHVoxGridRender(torch.autograd.Function):
     @staticmethod
     def forward(ctx, densities: Tensor, features: Tensor, origins: Tensor, directions: Tensor, grid: VoxelGrid, args: _kernels.RenderArgs):
         desc = grid.kernel_desc(densities, features)
-        colour, depth, acc, disparity = _kernels.render_forward(desc, origins, directions, args)
-        ctx.desc, ctx.args = desc, args
+        # When a backward pass will follow, the forward keeps (sigmoid(raw) rgb, sigma) of every contributing sample
+        # ([S, N, 4] fp32) so that the backward does not gather the 8 corner records a second time.
+        cache = None
+        n = origins.shape[0]
+        if (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]) and n > 0:
+            if _kernels.sample_cache_bytes(n, args.num_samples) <= sample_cache_limit_bytes():
+                cache = _kernels.new_sample_cache(n, args.num_samples, origins.device)
+        colour, depth, acc, disparity = _kernels.render_forward(desc, origins, directions, args, cache)
+        ctx.desc, ctx.args, ctx.cache = desc, args, cache
         ctx.save_for_backward(origins, directions, colour, depth, acc)
         ctx.set_materialize_grads(False)  # unused outputs arrive as None instead of zero tensors
         return colour, depth, acc, disparity
@@ -104,9 +112,17 @@ class _FusedSHVoxGridRender(torch.autograd.Function):
         grad_f = torch.zeros_like(desc.features) if need_f else None
         if need_d or need_f:
             _kernels.render_backward(
-                desc, origins, directions, ctx.args, (colour, depth, acc), (g_colour, g_depth, g_acc, g_disparity), grad_d, grad_f
+                desc, origins, directions, ctx.args, (colour, depth, acc), (g_colour, g_depth, g_acc, g_disparity), grad_d, grad_f,
+                ctx.cache,
             )
+        ctx.cache = None  # free the per-sample records as soon as they are consumed
         return grad_d, grad_f, None, None, None, None
+
+
+def sample_cache_limit_bytes() -> int:
+    """Upper bound on the per-call sample cache (``16 * rays * samples`` bytes); above it the backward re-gathers.
+    Default 16 GiB (a B200 has 180 GB); override with ``R3D_SAMPLE_CACHE_MAX_BYTES`` (0 disables the cache)."""
+    return int(os.environ.get("R3D_SAMPLE_CACHE_MAX_BYTES", 16 * 2**30))
 
 
 def _validate_config(cfg: SHVoxGridRenderConfig) -> None:
