@@ -414,7 +414,7 @@ struct CoopSmem {
 };
 
 template <int DEG, int VEC>
-__global__ void __launch_bounds__(128) render_bwd_coop_kernel(const GridP g, const RaysP rp, const CfgP c, const BwdP b) {
+__global__ void __launch_bounds__(128, DEG >= 3 ? 3 : 4) render_bwd_coop_kernel(const GridP g, const RaysP rp, const CfgP c, const BwdP b) {
   using S = CoopShape<DEG>;
   constexpr int K = S::K, F = S::F;
   constexpr unsigned FULL = 0xffffffffu;
@@ -558,50 +558,53 @@ __global__ void __launch_bounds__(128) render_bwd_coop_kernel(const GridP g, con
       const int L = __ffs(leaders) - 1;
       leaders &= leaders - 1;
       const unsigned members = __shfl_sync(FULL, peers, L);
-      if (b.gfeat) {
+      // One sweep over the cell's member samples accumulates, per lane, its float4 of up to PASSES corner records
+      // (the P row is loaded once and reused for every pass) and the density gradient of corner (lane & 7).
+      float4 a[S::PASSES];
+#pragma unroll
+      for (int pass = 0; pass < S::PASSES; ++pass) a[pass] = make_float4(0.f, 0.f, 0.f, 0.f);
+      float ad = 0.f;
+      unsigned mm = members;
+      while (mm) {
+        const int m = __ffs(mm) - 1;
+        mm &= mm - 1;
+        const float* Wm = sm.W + m * S::WROW;
+        ad = fmaf(Wm[lane & 7], sm.D[m], ad);
+        if (role_ok) {
+          const float4 p4 = *reinterpret_cast<const float4*>(sm.P + m * S::PROW + 4 * cj);
+#pragma unroll
+          for (int pass = 0; pass < S::PASSES; ++pass) {
+            const float wm = Wm[pass * S::CPP + cq];
+            a[pass].x = fmaf(wm, p4.x, a[pass].x), a[pass].y = fmaf(wm, p4.y, a[pass].y);
+            a[pass].z = fmaf(wm, p4.z, a[pass].z), a[pass].w = fmaf(wm, p4.w, a[pass].w);
+          }
+        }
+      }
+      const int* VL = sm.V + L * S::WROW;
+      if (b.gfeat && role_ok) {
 #pragma unroll
         for (int pass = 0; pass < S::PASSES; ++pass) {
-          const int corner = pass * S::CPP + cq;
-          if (role_ok) {
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-            unsigned mm = members;
-            while (mm) {
-              const int m = __ffs(mm) - 1;
-              mm &= mm - 1;
-              const float wm = sm.W[m * S::WROW + corner];
-              const float4 p4 = *reinterpret_cast<const float4*>(sm.P + m * S::PROW + 4 * cj);
-              a.x = fmaf(wm, p4.x, a.x), a.y = fmaf(wm, p4.y, a.y), a.z = fmaf(wm, p4.z, a.z), a.w = fmaf(wm, p4.w, a.w);
-            }
-            if (a.x != 0.f || a.y != 0.f || a.z != 0.f || a.w != 0.f) {
-              float* dst = b.gfeat + (size_t)sm.V[L * S::WROW + corner] * (size_t)g.stride + 4 * cj;
-              if constexpr (VEC != 0) {
-                red_add_v4(dst, a.x, a.y, a.z, a.w);
-              } else {
-                if (4 * cj + 0 < F) atomicAdd(dst + 0, a.x);
-                if (4 * cj + 1 < F) atomicAdd(dst + 1, a.y);
-                if (4 * cj + 2 < F) atomicAdd(dst + 2, a.z);
-                if (4 * cj + 3 < F) atomicAdd(dst + 3, a.w);
-              }
+          const float4 v = a[pass];
+          if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) {
+            float* dst = b.gfeat + (size_t)VL[pass * S::CPP + cq] * (size_t)g.stride + 4 * cj;
+            if constexpr (VEC != 0) {
+              red_add_v4(dst, v.x, v.y, v.z, v.w);
+            } else {
+              if (4 * cj + 0 < F) atomicAdd(dst + 0, v.x);
+              if (4 * cj + 1 < F) atomicAdd(dst + 1, v.y);
+              if (4 * cj + 2 < F) atomicAdd(dst + 2, v.z);
+              if (4 * cj + 3 < F) atomicAdd(dst + 3, v.w);
             }
           }
         }
       }
-      if (b.gdens && lane < 8) {
-        float a = 0.f;
-        unsigned mm = members;
-        while (mm) {
-          const int m = __ffs(mm) - 1;
-          mm &= mm - 1;
-          a = fmaf(sm.W[m * S::WROW + lane], sm.D[m], a);
+      if (b.gdens && lane < 8 && ad != 0.f) {
+        const int vx_ = VL[lane];
+        if (g.pre == R3D_PRE_ABS) {
+          const float v = __ldg(g.dens + vx_);
+          ad = (v > 0.f) ? ad : ((v < 0.f) ? -ad : 0.0f);  // d|x|/dx = sign(x), 0 at 0 (torch.abs)
         }
-        if (a != 0.f) {
-          const int vx_ = sm.V[L * S::WROW + lane];
-          if (g.pre == R3D_PRE_ABS) {
-            const float v = __ldg(g.dens + vx_);
-            a = (v > 0.f) ? a : ((v < 0.f) ? -a : 0.0f);  // d|x|/dx = sign(x), 0 at 0 (torch.abs)
-          }
-          atomicAdd(b.gdens + vx_, a);
-        }
+        atomicAdd(b.gdens + vx_, ad);
       }
     }
     __syncwarp();  // the tables are rewritten at the next contributing step
