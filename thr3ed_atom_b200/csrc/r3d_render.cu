@@ -171,6 +171,19 @@ __device__ __forceinline__ void corner_scatter(float* __restrict__ rec, const fl
   }
 }
 
+// lane layout shared by the warp-cooperative kernels: LPR lanes per voxel record, one float4 each
+template <int DEG>
+struct CoopShape {
+  static constexpr int K = (DEG + 1) * (DEG + 1);
+  static constexpr int F = 3 * K;
+  static constexpr int NV = (F + 3) / 4;                              // float4s of a record that carry data
+  static constexpr int LPR = NV <= 1 ? 1 : (NV <= 4 ? 4 : (NV <= 8 ? 8 : 16));  // lanes per record
+  static constexpr int CPP = (32 / LPR) < 8 ? (32 / LPR) : 8;        // corners per pass
+  static constexpr int PASSES = 8 / CPP;
+  static constexpr int PROW = (NV % 2) ? 4 * NV : 4 * NV + 4;         // row stride: odd multiple of 4 floats => conflict-free
+  static constexpr int WROW = 12;                                     // 8 used; 12 keeps 128-bit stores conflict-free
+};
+
 // =================================================================================================
 // forward
 // =================================================================================================
@@ -232,6 +245,190 @@ __global__ void __launch_bounds__(128) render_fwd_kernel(const GridP g, const Ra
   out.depth[ray] = dep;
   out.acc[ray] = acc;
   if (out.disparity) {  // accumulate.py:85-88; 0/0 stays NaN through torch.maximum
+    const float ratio = __fdiv_rn(dep, acc);
+    const float m = (ratio != ratio) ? ratio : fmaxf(kZeroPlus, ratio);
+    out.disparity[ray] = __fdiv_rn(1.0f, m);
+  }
+}
+
+
+// =================================================================================================
+// forward, warp-cooperative gather (default for the padded layouts, non-diffuse)
+//
+// Profile of the thread-per-ray gather (profiles/r01_v0_ncu_full_summary.md, l1tex__data_pipe_lsu_wavefronts 94 %):
+// the L1 data pipe spends one wavefront per distinct 128-byte line a request touches; with one ray per lane a 32-lane
+// LDG.128 touches ~10 voxel records to deliver 16 bytes from each, 56 times per marching step.  Here the warp first
+// finds the distinct interpolation cells among its contributing samples (__match_any_sync), copies each such cell's 8
+// corner records global -> shared with cp.async, consecutive lanes covering consecutive 16-byte pieces of one record
+// (a record costs one or two wavefronts instead of one per lane per piece), and then every ray reads its cell's
+// records from shared memory.  The maths per ray is unchanged (same order of operations as render_fwd_kernel).
+// =================================================================================================
+template <int DEG>
+struct FwdStageShape {
+  using S = CoopShape<DEG>;
+  static constexpr int SLOTS = DEG >= 3 ? 4 : 8;       // distinct cells staged per round (static smem <= 48 KB)
+  static constexpr int REC = 4 * S::NV;                // floats staged per record
+  static constexpr int SLOT = 8 * REC + 4;             // (SLOT / 4) odd: 128-bit reads of different slots hit different banks
+  static constexpr int PER_SLOT = 8 * S::NV;           // float4 copies per cell
+};
+
+template <int DEG>
+struct FwdStageSmem {
+  using H = FwdStageShape<DEG>;
+  float rec[H::SLOTS * H::SLOT];
+  int vox[H::SLOTS * 8];
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int DEG>
+__global__ void __launch_bounds__(128, DEG >= 3 ? 3 : 4) render_fwd_coop_kernel(const GridP g, const RaysP rp, const CfgP c, const OutP out) {
+  using H = FwdStageShape<DEG>;
+  using S = CoopShape<DEG>;
+  constexpr int K = S::K, NV = S::NV;
+  constexpr unsigned FULL = 0xffffffffu;
+  __shared__ __align__(16) FwdStageSmem<DEG> smem_all[4];
+  FwdStageSmem<DEG>& sm = smem_all[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
+
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long ray = thread_to_ray(rp, t);
+  bool alive = ray >= 0;
+  RayCtx s;
+  float Y[K];
+  s.i_lo = 1, s.i_hi = 0;
+  if (alive) {
+    float vx, vy, vz;
+    setup_ray(g, rp, c, ray, s, vx, vy, vz);
+    sh_basis<DEG>(vx, vy, vz, Y);
+  }
+  const Ray& r = s.r;
+  bool marching = alive && s.i_lo <= s.i_hi;
+  int lo = marching ? s.i_lo : 0x7fffffff, hi = marching ? s.i_hi : -1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = min(lo, __shfl_xor_sync(FULL, lo, o));
+    hi = max(hi, __shfl_xor_sync(FULL, hi, o));
+  }
+
+  float T = 1.0f, cr = 0.f, cg = 0.f, cb = 0.f, dep = 0.f, acc = 0.f;
+  float z = 0.f;
+  bool have_z = false;
+  for (int i = lo; i <= hi; ++i) {
+    // ---- per-lane: position, inside test, cell, density ----
+    bool contributes = false;
+    float wc[8];
+    int vox[8];
+    float sigma = 0.f, zn = 0.f;
+    bool last = false;
+    int key = -1;
+    const bool mine = marching && i >= s.i_lo && i <= s.i_hi;
+    if (mine) {
+      if (!have_z) z = s.dg.at(i), have_z = true;
+      last = (i == c.S - 1);
+      zn = last ? 0.0f : s.dg.at(i + 1);
+      const float px = __fadd_rn(r.ox, __fmul_rn(r.dx, z));
+      const float py = __fadd_rn(r.oy, __fmul_rn(r.dy, z));
+      const float pz = __fadd_rn(r.oz, __fmul_rn(r.dz, z));
+      if (inside_aabb(g, px, py, pz)) {
+        Cell cell;
+        make_cell(g, px, py, pz, cell);
+        float dpost;
+        sigma = density_post(g.post, density_pre_interp(g, cell), dpost);
+        if (sigma != 0.0f) {
+          contributes = true;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int ix = k >> 2, iy = (k >> 1) & 1, iz = k & 1;
+            wc[k] = cell.wx[ix] * cell.wy[iy] * cell.wz[iz];
+            vox[k] = cell.ox[ix] + cell.oy[iy] + cell.oz[iz];
+          }
+          key = vox[0] ^ ((cell.wx[0] != 0.f) << 28) ^ ((cell.wy[0] != 0.f) << 29) ^ ((cell.wz[0] != 0.f) << 30);
+        }
+      }
+    }
+    const unsigned act = __ballot_sync(FULL, contributes);
+    if (act != 0u) {
+      // ---- group the contributing samples by cell; every distinct cell gets a staging slot ----
+      unsigned peers = 0u;
+      if (contributes) peers = __match_any_sync(act, key);
+      const int leader_lane = contributes ? (__ffs(peers) - 1) : 0;
+      const bool leader = contributes && leader_lane == lane;
+      const unsigned leaders = __ballot_sync(FULL, leader);
+      const int num_cells = __popc(leaders);
+      const int my_slot = __popc(leaders & ((1u << leader_lane) - 1u));
+      float rr = 0.f, rg = 0.f, rb = 0.f;
+      for (int sb = 0; sb < num_cells; sb += H::SLOTS) {
+        const int n = min(H::SLOTS, num_cells - sb);
+        if (leader && my_slot >= sb && my_slot < sb + H::SLOTS) {
+          int* v = sm.vox + (my_slot - sb) * 8;
+          *reinterpret_cast<int4*>(v) = make_int4(vox[0], vox[1], vox[2], vox[3]);
+          *reinterpret_cast<int4*>(v + 4) = make_int4(vox[4], vox[5], vox[6], vox[7]);
+        }
+        __syncwarp();
+        // ---- stage n cells x 8 records: lane q copies 16 bytes; consecutive lanes walk along one record ----
+        for (int q = lane; q < n * H::PER_SLOT; q += 32) {
+          const int slot = q / H::PER_SLOT, rem = q - slot * H::PER_SLOT;
+          const int corner = rem / NV, j = rem - corner * NV;
+          const float* src = g.feat + (size_t)sm.vox[slot * 8 + corner] * (size_t)g.stride + 4 * j;
+          cp_async16(sm.rec + slot * H::SLOT + corner * H::REC + 4 * j, src);
+        }
+        cp_async_wait_all();
+        __syncwarp();
+        // ---- every ray whose cell is staged contracts its 8 corner records with its own SH basis ----
+        if (contributes && my_slot >= sb && my_slot < sb + H::SLOTS) {
+          const float* base = sm.rec + (my_slot - sb) * H::SLOT;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float* rec = base + k * H::REC;
+            float v[4 * NV];
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+              const float4 q4 = *reinterpret_cast<const float4*>(rec + 4 * j);
+              v[4 * j] = q4.x, v[4 * j + 1] = q4.y, v[4 * j + 2] = q4.z, v[4 * j + 3] = q4.w;
+            }
+            float sr = 0.f, sg = 0.f, sbl = 0.f;
+#pragma unroll
+            for (int kk = 0; kk < K; ++kk) {
+              sr = fmaf(Y[kk], v[kk], sr);
+              sg = fmaf(Y[kk], v[K + kk], sg);
+              sbl = fmaf(Y[kk], v[2 * K + kk], sbl);
+            }
+            rr = fmaf(wc[k], sr, rr), rg = fmaf(wc[k], sg, rg), rb = fmaf(wc[k], sbl, rb);
+          }
+        }
+        __syncwarp();  // the slots are overwritten by the next round / the next marching step
+      }
+      if (contributes) {
+        const float delta = last ? __fmul_rn(kInfinity, s.dnorm) : __fmul_rn(__fsub_rn(zn, z), s.dnorm);
+        const float alpha = 1.0f - expf(-(sigma * delta));
+        const float w = alpha * T;
+        const float sr = sigmoidf_(rr), sg = sigmoidf_(rg), sb2 = sigmoidf_(rb);
+        if (out.cache) out.cache[(size_t)i * rp.n + ray] = make_float4(sr, sg, sb2, sigma);
+        cr = fmaf(w, sr, cr);
+        cg = fmaf(w, sg, cg);
+        cb = fmaf(w, sb2, cb);
+        dep = fmaf(w, z, dep);
+        acc += w;
+        T *= (1.0f - alpha);
+        if (T == 0.0f) marching = false;  // every later weight is alpha*0 = 0 exactly
+      }
+    }
+    if (mine) z = zn;
+  }
+  if (!alive) return;
+  if (c.flags & R3D_FLAG_WHITE_BKGD) {
+    const float bg = 1.0f - acc;
+    cr += bg, cg += bg, cb += bg;
+  }
+  out.colour[3 * ray] = cr, out.colour[3 * ray + 1] = cg, out.colour[3 * ray + 2] = cb;
+  out.depth[ray] = dep;
+  out.acc[ray] = acc;
+  if (out.disparity) {
     const float ratio = __fdiv_rn(dep, acc);
     const float m = (ratio != ratio) ? ratio : fmaxf(kZeroPlus, ratio);
     out.disparity[ray] = __fdiv_rn(1.0f, m);
@@ -392,18 +589,6 @@ __global__ void __launch_bounds__(128) render_bwd_kernel(const GridP g, const Ra
 //      issues ONE 128-bit reduction per lane: a record is one coalesced, fully used line instead of 32 scattered
 //      lanes, and samples sharing a cell are summed before they reach L2.
 // =================================================================================================
-template <int DEG>
-struct CoopShape {
-  static constexpr int K = (DEG + 1) * (DEG + 1);
-  static constexpr int F = 3 * K;
-  static constexpr int NV = (F + 3) / 4;                              // float4s of a record that carry data
-  static constexpr int LPR = NV <= 1 ? 1 : (NV <= 4 ? 4 : (NV <= 8 ? 8 : 16));  // lanes per record
-  static constexpr int CPP = (32 / LPR) < 8 ? (32 / LPR) : 8;        // corners per pass
-  static constexpr int PASSES = 8 / CPP;
-  static constexpr int PROW = (NV % 2) ? 4 * NV : 4 * NV + 4;         // row stride: odd multiple of 4 floats => conflict-free
-  static constexpr int WROW = 12;                                     // 8 used; 12 keeps 128-bit stores conflict-free
-};
-
 template <int DEG>
 struct CoopSmem {
   using S = CoopShape<DEG>;
@@ -642,7 +827,14 @@ __global__ void __launch_bounds__(128) mark_touched_kernel(const GridP g, const 
 // host-side dispatch
 // =================================================================================================
 template <int DEG>
-static void launch_fwd(int vec, dim3 grid, cudaStream_t st, const GridP& g, const RaysP& r, const CfgP& c, const OutP& o) {
+static void launch_fwd(int vec, int variant, dim3 grid, cudaStream_t st, const GridP& g, const RaysP& r, const CfgP& c, const OutP& o) {
+  // cooperative gather needs 16-byte aligned records; band-0-only (diffuse) renders read 3 floats per record and
+  // keep the per-ray gather
+  const bool diffuse = (c.flags & R3D_FLAG_DIFFUSE) != 0 && DEG > 0;
+  if (vec != 0 && !diffuse && !(variant & 2)) {
+    render_fwd_coop_kernel<DEG><<<grid, 128, 0, st>>>(g, r, c, o);
+    return;
+  }
   if (vec == 8)
     render_fwd_kernel<DEG, 8><<<grid, 128, 0, st>>>(g, r, c, o);
   else if (vec == 4)
@@ -707,10 +899,10 @@ extern "C" int r3d_render_fwd(const R3dGrid* grid, const R3dRays* rays, const R3
   const int vec = vector_width(g, nullptr);
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   switch (grid->sh_degree) {
-    case 0: launch_fwd<0>(vec, blocks, st, g, r, c, o); break;
-    case 1: launch_fwd<1>(vec, blocks, st, g, r, c, o); break;
-    case 2: launch_fwd<2>(vec, blocks, st, g, r, c, o); break;
-    default: launch_fwd<3>(vec, blocks, st, g, r, c, o); break;
+    case 0: launch_fwd<0>(vec, cfg->variant, blocks, st, g, r, c, o); break;
+    case 1: launch_fwd<1>(vec, cfg->variant, blocks, st, g, r, c, o); break;
+    case 2: launch_fwd<2>(vec, cfg->variant, blocks, st, g, r, c, o); break;
+    default: launch_fwd<3>(vec, cfg->variant, blocks, st, g, r, c, o); break;
   }
   return check_launch("r3d_render_fwd");
 }
