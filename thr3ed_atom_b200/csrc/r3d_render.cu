@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(128) render_fwd_kernel(const GridP g, const Ra
 // the L1 data pipe spends one wavefront per distinct 128-byte line a request touches; with one ray per lane a 32-lane
 // LDG.128 touches ~10 voxel records to deliver 16 bytes from each, 56 times per marching step.  Here the warp first
 // finds the distinct interpolation cells among its contributing samples (__match_any_sync), copies each such cell's 8
-// corner records global -> shared with cp.async, consecutive lanes covering consecutive 16-byte pieces of one record
+// corner records global -> shared, consecutive lanes covering consecutive 16-byte pieces of one record
 // (a record costs one or two wavefronts instead of one per lane per piece), and then every ray reads its cell's
 // records from shared memory.  The maths per ray is unchanged (same order of operations as render_fwd_kernel).
 // =================================================================================================
@@ -314,6 +314,10 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : 4) render_fwd_coop_kernel(
     lo = min(lo, __shfl_xor_sync(FULL, lo, o));
     hi = max(hi, __shfl_xor_sync(FULL, hi, o));
   }
+
+  // staging role of this lane: float4 `cj` of corner `pass * CPP + cq`
+  const int cq = lane / S::LPR, cj = lane % S::LPR;
+  const bool role_ok = (cq < S::CPP) && (cj < S::NV);
 
   float T = 1.0f, cr = 0.f, cg = 0.f, cb = 0.f, dep = 0.f, acc = 0.f;
   float z = 0.f;
@@ -370,12 +374,18 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : 4) render_fwd_coop_kernel(
           *reinterpret_cast<int4*>(v + 4) = make_int4(vox[4], vox[5], vox[6], vox[7]);
         }
         __syncwarp();
-        // ---- stage n cells x 8 records: lane q copies 16 bytes; consecutive lanes walk along one record ----
-        for (int q = lane; q < n * H::PER_SLOT; q += 32) {
-          const int slot = q / H::PER_SLOT, rem = q - slot * H::PER_SLOT;
-          const int corner = rem / NV, j = rem - corner * NV;
-          const float* src = g.feat + (size_t)sm.vox[slot * 8 + corner] * (size_t)g.stride + 4 * j;
-          cp_async16(sm.rec + slot * H::SLOT + corner * H::REC + 4 * j, src);
+        // ---- stage n cells x 8 records with cp.async (all copies of the round in flight, one wait).  Fixed lane
+        //      roles (LPR lanes per record, one 16-byte piece each, CPP records per request): a request reads whole
+        //      records with consecutive lanes and lands them contiguously in shared memory.
+        if (role_ok) {
+          for (int slot = 0; slot < n; ++slot) {
+#pragma unroll
+            for (int pass = 0; pass < S::PASSES; ++pass) {
+              const int corner = pass * S::CPP + cq;
+              cp_async16(sm.rec + slot * H::SLOT + corner * H::REC + 4 * cj,
+                         g.feat + (size_t)sm.vox[slot * 8 + corner] * (size_t)g.stride + 4 * cj);
+            }
+          }
         }
         cp_async_wait_all();
         __syncwarp();
