@@ -152,8 +152,8 @@ def test_point_lookup_matches_reference(name, cuda_device):
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["deg2_16cube", "c1_32cube_deg0"])
 def test_unpadded_reference_layout_gives_the_same_result(name, cuda_device):
-    """The C ABI accepts any record stride: whole 32-byte sectors (256-bit loads, what VoxelGrid stores), whole 16-byte
-    vectors (128-bit loads) and the reference's unpadded layout (scalar loads).  All three give the same result."""
+    """The C ABI accepts any record stride: whole 16-byte vectors (what VoxelGrid stores), whole 32-byte sectors
+    (256-bit loads in the per-ray kernels) and the reference's unpadded layout (scalar loads).  All give the same result."""
     from thr3ed_atom_b200 import _kernels
     from thr3ed_atom_b200.thre3d_reprs.renderers import make_render_args
 
@@ -163,8 +163,8 @@ def test_unpadded_reference_layout_gives_the_same_result(name, cuda_device):
     nf = inp["features"].shape[-1]
     padded = grid.kernel_desc()
     unpadded = dataclasses.replace(padded, features=torch.from_numpy(inp["features"]).to(cuda_device).contiguous())
-    stride4 = (nf + 3) // 4 * 4
-    vec4 = torch.zeros((*inp["features"].shape[:3], stride4), device=cuda_device)
+    stride8 = (nf + 7) // 8 * 8
+    vec4 = torch.zeros((*inp["features"].shape[:3], stride8), device=cuda_device)
     vec4[..., :nf] = unpadded.features
     vec4 = dataclasses.replace(padded, features=vec4)
     assert padded.features.shape[-1] % 4 == 0 and unpadded.features.shape[-1] % 4 != 0
@@ -465,3 +465,33 @@ def test_config3_shape_properties(cuda_device):
     (sub.colour * gc.to(cuda_device)).sum().backward()
     assert rel_l2(grid.feature_storage.grad[..., :27].cpu().numpy(), want["grad_features"].numpy()) < 1e-4
     assert rel_l2(grid.densities.grad.cpu().numpy(), want["grad_densities"].numpy()) < 1e-4
+
+
+@pytest.mark.parametrize("name", ["deg2_16cube", "deg3_abs", "deg1_aniso_softplus", "c1_32cube_deg0", "deg2_jitter_optimized"])
+def test_cooperative_and_per_ray_kernels_agree(name, cuda_device, monkeypatch):
+    """The warp-cooperative kernels (default) against the thread-per-ray kernels (variant 3), with and without the
+    forward's sample cache: same per-ray arithmetic => bit-identical images, gradients equal up to summation order."""
+    from thr3ed_atom_b200.thre3d_reprs.renderers import render_hints, render_sh_voxel_grid
+
+    case = CASES[name]
+    inp = build_inputs(case)
+    gc = torch.from_numpy(inp["grad_colour"]).to(cuda_device)
+    results = {}
+    for label, variant, cache_limit in (("coop+cache", 0, None), ("per-ray+cache", 3, None), ("coop", 0, "0"), ("per-ray", 3, "0")):
+        if cache_limit is None:
+            monkeypatch.delenv("R3D_SAMPLE_CACHE_MAX_BYTES", raising=False)
+        else:
+            monkeypatch.setenv("R3D_SAMPLE_CACHE_MAX_BYTES", cache_limit)
+        grid = make_cuda_grid(case, inp, cuda_device)
+        hints = {"variant": variant}
+        if case.jitter:
+            hints["jitter"] = torch.from_numpy(inp["jitter"]).to(cuda_device)
+        with render_hints(**hints):
+            out = render_sh_voxel_grid(grid, _rays(inp, cuda_device), make_cuda_config(case))
+            (out.colour * gc).sum().backward()
+        results[label] = (out.colour.detach().clone(), out.depth.detach().clone(), grid.densities.grad.clone(), grid.feature_storage.grad.clone())
+    ref = results["per-ray"]
+    for label, res in results.items():
+        assert torch.equal(res[0], ref[0]) and torch.equal(res[1], ref[1]), label
+        assert rel_l2(res[2].cpu().numpy(), ref[2].cpu().numpy()) < 1e-5, label
+        assert rel_l2(res[3].cpu().numpy(), ref[3].cpu().numpy()) < 1e-5, label

@@ -60,8 +60,8 @@ def _grid(deg=2, dims=(4, 5, 6), tunable=True, **kw):
 
 
 # ---------------------------------------------------------------------------- VoxelGrid
-@pytest.mark.parametrize("deg,stride", [(0, 4), (1, 16), (2, 32), (3, 48)])
-def test_feature_storage_is_padded_to_whole_sectors(deg, stride):
+@pytest.mark.parametrize("deg,stride", [(0, 4), (1, 12), (2, 28), (3, 48)])
+def test_feature_storage_is_padded_to_whole_16_byte_vectors(deg, stride):
     grid = _grid(deg)
     nf = 3 * (deg + 1) ** 2
     assert padded_feature_stride(nf) == stride
