@@ -36,13 +36,18 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found (set $NVCC)")
 
 
+def _extra_flags():
+    """Extra nvcc flags from $R3D_NVCC_FLAGS (tuning experiments, e.g. "-DR3D_FWD_BLOCKS=5")."""
+    return os.environ.get("R3D_NVCC_FLAGS", "").split()
+
+
 def _source_digest() -> str:
     h = hashlib.sha256()
     files = sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + list(INCLUDE.glob("*.h")))
     for f in files:
         h.update(f.name.encode())
         h.update(f.read_bytes())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(NVCC_FLAGS + _extra_flags()).encode())
     return h.hexdigest()
 
 
@@ -55,7 +60,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and is_current():
         return LIB_PATH
     LIB_DIR.mkdir(exist_ok=True)
-    cmd = [_nvcc(), *NVCC_FLAGS, f"-I{INCLUDE}", f"-I{CSRC}", "-o", str(LIB_PATH)]
+    cmd = [_nvcc(), *NVCC_FLAGS, *_extra_flags(), f"-I{INCLUDE}", f"-I{CSRC}", "-o", str(LIB_PATH)]
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += [str(CSRC / s) for s in SOURCES]

@@ -20,6 +20,15 @@
 // (SURVEY.md A.6).  Gradients are scattered with 128-bit vector reductions (red.global.add.v4.f32).
 #include "r3d_host.h"
 
+// resident CTAs per SM the cooperative kernels are compiled for (register budget = 65536 / (128 * blocks)).
+// Measured at c3 on the B200: backward 7.95 ms at 4, 7.45 ms at 5 (96 registers, ~40 bytes of spill); forward unchanged.
+#ifndef R3D_FWD_BLOCKS
+#define R3D_FWD_BLOCKS 4
+#endif
+#ifndef R3D_BWD_BLOCKS
+#define R3D_BWD_BLOCKS 5
+#endif
+
 namespace r3d {
 
 struct OutP {
@@ -286,7 +295,7 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 template <int DEG>
-__global__ void __launch_bounds__(128, DEG >= 3 ? 3 : 4) render_fwd_coop_kernel(const GridP g, const RaysP rp, const CfgP c, const OutP out) {
+__global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_FWD_BLOCKS) render_fwd_coop_kernel(const GridP g, const RaysP rp, const CfgP c, const OutP out) {
   using H = FwdStageShape<DEG>;
   using S = CoopShape<DEG>;
   constexpr int K = S::K, NV = S::NV;
@@ -609,7 +618,7 @@ struct CoopSmem {
 };
 
 template <int DEG, int VEC>
-__global__ void __launch_bounds__(128, DEG >= 3 ? 3 : 4) render_bwd_coop_kernel(const GridP g, const RaysP rp, const CfgP c, const BwdP b) {
+__global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_BWD_BLOCKS) render_bwd_coop_kernel(const GridP g, const RaysP rp, const CfgP c, const BwdP b) {
   using S = CoopShape<DEG>;
   constexpr int K = S::K, F = S::F;
   constexpr unsigned FULL = 0xffffffffu;
