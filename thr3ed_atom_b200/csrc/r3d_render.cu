@@ -611,7 +611,7 @@ __global__ void __launch_bounds__(128) render_bwd_kernel(const GridP g, const Ra
 template <int DEG>
 struct CoopSmem {
   using S = CoopShape<DEG>;
-  float P[32 * S::PROW];
+  float P[32 * S::PROW + 64];  // +64: lanes whose float4 index is past the record still read in bounds
   float W[32 * S::WROW];
   int V[32 * S::WROW];
   float D[32];
@@ -658,6 +658,9 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_BWD_BLOCKS) render_bwd
   // cooperative-phase role of this lane: float4 `cj` of corner `pass * CPP + cq`
   const int cq = lane / S::LPR, cj = lane % S::LPR;
   const bool role_ok = (cq < S::CPP) && (cj < S::NV);
+  // in a band-0-only (diffuse) render only the float4s holding a k = 0 coefficient (elements 0, K, 2K) carry gradient
+  const bool band_ok = !(DEG > 0 && diffuse) || (cj == 0) || (cj == K / 4) || (cj == (2 * K) / 4);
+  const unsigned ustride = (unsigned)g.stride;
 
   float T = 1.0f, prefix = 0.f;
   float z = 0.f;
@@ -763,7 +766,8 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_BWD_BLOCKS) render_bwd
       leaders &= leaders - 1;
       const unsigned members = __shfl_sync(FULL, peers, L);
       // One sweep over the cell's member samples accumulates, per lane, its float4 of up to PASSES corner records
-      // (the P row is loaded once and reused for every pass) and the density gradient of corner (lane & 7).
+      // (the P row is loaded once and reused for every pass) and the density gradient of corner (lane & 7).  Every lane
+      // runs the sweep (lanes without a role read in-bounds garbage and never store): no divergence inside the loop.
       float4 a[S::PASSES];
 #pragma unroll
       for (int pass = 0; pass < S::PASSES; ++pass) a[pass] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -774,36 +778,33 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_BWD_BLOCKS) render_bwd
         mm &= mm - 1;
         const float* Wm = sm.W + m * S::WROW;
         ad = fmaf(Wm[lane & 7], sm.D[m], ad);
-        if (role_ok) {
-          const float4 p4 = *reinterpret_cast<const float4*>(sm.P + m * S::PROW + 4 * cj);
+        const float4 p4 = *reinterpret_cast<const float4*>(sm.P + m * S::PROW + 4 * cj);
 #pragma unroll
-          for (int pass = 0; pass < S::PASSES; ++pass) {
-            const float wm = Wm[pass * S::CPP + cq];
-            a[pass].x = fmaf(wm, p4.x, a[pass].x), a[pass].y = fmaf(wm, p4.y, a[pass].y);
-            a[pass].z = fmaf(wm, p4.z, a[pass].z), a[pass].w = fmaf(wm, p4.w, a[pass].w);
-          }
+        for (int pass = 0; pass < S::PASSES; ++pass) {
+          const float wm = Wm[(pass * S::CPP + cq) & 7];
+          a[pass].x = fmaf(wm, p4.x, a[pass].x), a[pass].y = fmaf(wm, p4.y, a[pass].y);
+          a[pass].z = fmaf(wm, p4.z, a[pass].z), a[pass].w = fmaf(wm, p4.w, a[pass].w);
         }
       }
       const int* VL = sm.V + L * S::WROW;
-      if (b.gfeat && role_ok) {
+      if (b.gfeat && role_ok && band_ok) {
 #pragma unroll
         for (int pass = 0; pass < S::PASSES; ++pass) {
           const float4 v = a[pass];
-          if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) {
-            float* dst = b.gfeat + (size_t)VL[pass * S::CPP + cq] * (size_t)g.stride + 4 * cj;
-            if constexpr (VEC != 0) {
-              red_add_v4(dst, v.x, v.y, v.z, v.w);
-            } else {
-              if (4 * cj + 0 < F) atomicAdd(dst + 0, v.x);
-              if (4 * cj + 1 < F) atomicAdd(dst + 1, v.y);
-              if (4 * cj + 2 < F) atomicAdd(dst + 2, v.z);
-              if (4 * cj + 3 < F) atomicAdd(dst + 3, v.w);
-            }
+          // 32x32 -> 64-bit unsigned multiply: record offsets exceed 2^31 floats at 512^3 / degree 3
+          float* dst = b.gfeat + (size_t)(unsigned)VL[pass * S::CPP + cq] * (size_t)ustride + 4 * cj;
+          if constexpr (VEC != 0) {
+            red_add_v4(dst, v.x, v.y, v.z, v.w);
+          } else {
+            if (4 * cj + 0 < F) atomicAdd(dst + 0, v.x);
+            if (4 * cj + 1 < F) atomicAdd(dst + 1, v.y);
+            if (4 * cj + 2 < F) atomicAdd(dst + 2, v.z);
+            if (4 * cj + 3 < F) atomicAdd(dst + 3, v.w);
           }
         }
       }
       if (b.gdens && lane < 8 && ad != 0.f) {
-        const int vx_ = VL[lane];
+        const unsigned vx_ = (unsigned)VL[lane];
         if (g.pre == R3D_PRE_ABS) {
           const float v = __ldg(g.dens + vx_);
           ad = (v > 0.f) ? ad : ((v < 0.f) ? -ad : 0.0f);  // d|x|/dx = sign(x), 0 at 0 (torch.abs)

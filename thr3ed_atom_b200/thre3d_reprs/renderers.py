@@ -121,8 +121,8 @@ class _FusedSHVoxGridRender(torch.autograd.Function):
 
 def sample_cache_limit_bytes() -> int:
     """Upper bound on the per-call sample cache (``16 * rays * samples`` bytes); above it the backward re-gathers.
-    Default 16 GiB (a B200 has 180 GB); override with ``R3D_SAMPLE_CACHE_MAX_BYTES`` (0 disables the cache)."""
-    return int(os.environ.get("R3D_SAMPLE_CACHE_MAX_BYTES", 16 * 2**30))
+    Default 48 GiB (a B200 has 180 GB); override with ``R3D_SAMPLE_CACHE_MAX_BYTES`` (0 disables the cache)."""
+    return int(os.environ.get("R3D_SAMPLE_CACHE_MAX_BYTES", 48 * 2**30))
 
 
 def _validate_config(cfg: SHVoxGridRenderConfig) -> None:
