@@ -477,7 +477,8 @@ def test_cooperative_and_per_ray_kernels_agree(name, cuda_device, monkeypatch):
     inp = build_inputs(case)
     gc = torch.from_numpy(inp["grad_colour"]).to(cuda_device)
     results = {}
-    for label, variant, cache_limit in (("coop+cache", 0, None), ("per-ray+cache", 3, None), ("coop", 0, "0"), ("per-ray", 3, "0")):
+    for label, variant, cache_limit in (("coop+cache", 0, None), ("per-ray+cache", 3, None), ("coop", 0, "0"), ("per-ray", 3, "0"),
+                                        ("coop, TMA staging", 4, None)):
         if cache_limit is None:
             monkeypatch.delenv("R3D_SAMPLE_CACHE_MAX_BYTES", raising=False)
         else:

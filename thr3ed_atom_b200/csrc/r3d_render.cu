@@ -282,10 +282,11 @@ struct FwdStageShape {
 };
 
 template <int DEG>
-struct FwdStageSmem {
+struct alignas(16) FwdStageSmem {  // one per warp: keep every warp's tables 16-byte aligned
   using H = FwdStageShape<DEG>;
   float rec[H::SLOTS * H::SLOT];
   int vox[H::SLOTS * 8];
+  unsigned long long mbar;  // completion barrier of the TMA (cp.async.bulk) staging variant
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
@@ -294,7 +295,31 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-template <int DEG>
+// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) with mbarrier completion ----
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <int DEG, bool TMA>
 __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_FWD_BLOCKS) render_fwd_coop_kernel(const GridP g, const RaysP rp, const CfgP c, const OutP out) {
   using H = FwdStageShape<DEG>;
   using S = CoopShape<DEG>;
@@ -303,6 +328,12 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_FWD_BLOCKS) render_fwd
   __shared__ __align__(16) FwdStageSmem<DEG> smem_all[4];
   FwdStageSmem<DEG>& sm = smem_all[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
+  unsigned tma_phase = 0;
+  if constexpr (TMA) {
+    if (lane == 0) mbar_init(&sm.mbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+  }
 
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long ray = thread_to_ray(rp, t);
@@ -386,17 +417,32 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_FWD_BLOCKS) render_fwd
         // ---- stage n cells x 8 records with cp.async (all copies of the round in flight, one wait).  Fixed lane
         //      roles (LPR lanes per record, one 16-byte piece each, CPP records per request): a request reads whole
         //      records with consecutive lanes and lands them contiguously in shared memory.
-        if (role_ok) {
-          for (int slot = 0; slot < n; ++slot) {
+        if constexpr (TMA) {
+          // one TMA bulk copy per record (REC*4 bytes, 16-byte aligned on both sides), completion counted on the
+          // warp's mbarrier: the staging traffic goes L2 -> shared memory without passing through the LSU data pipe
+          constexpr unsigned kRecBytes = H::REC * 4;
+          if (lane == 0) mbar_expect_tx(&sm.mbar, (unsigned)n * 8u * kRecBytes);
+          __syncwarp();
+          for (int q = lane; q < n * 8; q += 32) {
+            const int slot = q >> 3, corner = q & 7;
+            tma_bulk_g2s(sm.rec + slot * H::SLOT + corner * H::REC,
+                         g.feat + (size_t)(unsigned)sm.vox[slot * 8 + corner] * (size_t)(unsigned)g.stride, kRecBytes, &sm.mbar);
+          }
+          mbar_wait(&sm.mbar, tma_phase);
+          tma_phase ^= 1u;
+        } else {
+          if (role_ok) {
+            for (int slot = 0; slot < n; ++slot) {
 #pragma unroll
-            for (int pass = 0; pass < S::PASSES; ++pass) {
-              const int corner = pass * S::CPP + cq;
-              cp_async16(sm.rec + slot * H::SLOT + corner * H::REC + 4 * cj,
-                         g.feat + (size_t)sm.vox[slot * 8 + corner] * (size_t)g.stride + 4 * cj);
+              for (int pass = 0; pass < S::PASSES; ++pass) {
+                const int corner = pass * S::CPP + cq;
+                cp_async16(sm.rec + slot * H::SLOT + corner * H::REC + 4 * cj,
+                           g.feat + (size_t)(unsigned)sm.vox[slot * 8 + corner] * (size_t)(unsigned)g.stride + 4 * cj);
+              }
             }
           }
+          cp_async_wait_all();
         }
-        cp_async_wait_all();
         __syncwarp();
         // ---- every ray whose cell is staged contracts its 8 corner records with its own SH basis ----
         if (contributes && my_slot >= sb && my_slot < sb + H::SLOTS) {
@@ -420,6 +466,7 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_FWD_BLOCKS) render_fwd
             rr = fmaf(wc[k], sr, rr), rg = fmaf(wc[k], sg, rg), rb = fmaf(wc[k], sbl, rb);
           }
         }
+        if constexpr (TMA) fence_proxy_async_smem();  // generic-proxy reads above, async-proxy writes next
         __syncwarp();  // the slots are overwritten by the next round / the next marching step
       }
       if (contributes) {
@@ -609,7 +656,7 @@ __global__ void __launch_bounds__(128) render_bwd_kernel(const GridP g, const Ra
 //      lanes, and samples sharing a cell are summed before they reach L2.
 // =================================================================================================
 template <int DEG>
-struct CoopSmem {
+struct alignas(16) CoopSmem {
   using S = CoopShape<DEG>;
   float P[32 * S::PROW + 64];  // +64: lanes whose float4 index is past the record still read in bounds
   float W[32 * S::WROW];
@@ -852,7 +899,10 @@ static void launch_fwd(int vec, int variant, dim3 grid, cudaStream_t st, const G
   // keep the per-ray gather
   const bool diffuse = (c.flags & R3D_FLAG_DIFFUSE) != 0 && DEG > 0;
   if (vec != 0 && !diffuse && !(variant & 2)) {
-    render_fwd_coop_kernel<DEG><<<grid, 128, 0, st>>>(g, r, c, o);
+    if (variant & 4)  // TMA (cp.async.bulk) staging instead of per-lane cp.async: measured, see DESIGN.md
+      render_fwd_coop_kernel<DEG, true><<<grid, 128, 0, st>>>(g, r, c, o);
+    else
+      render_fwd_coop_kernel<DEG, false><<<grid, 128, 0, st>>>(g, r, c, o);
     return;
   }
   if (vec == 8)
