@@ -202,6 +202,8 @@ def main():
     ap.add_argument("--no-perturb", action="store_true")
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--flat-order", action="store_true", help="do not pass the image-shape hint (rays in list order)")
+    ap.add_argument("--reducer", default=os.environ.get("R3D_BENCH_REDUCER", "nccl"), choices=["nccl", "nvls"],
+                    help="N>1: gradient exchange = NCCL all-reduce, or the in-switch multimem kernel (csrc/r3d_comm.cu)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -290,11 +292,21 @@ def main():
     _renderers._kernels.render_backward = counted(timed("bwd", real_bwd))
 
     params = list(voxel_grid.parameters())
+    reducer = None
+    if world > 1 and args.reducer == "nvls":
+        from thr3ed_atom_b200.distributed import NVLSGradientReducer
+
+        reducer = NVLSGradientReducer(voxel_grid)  # gradients live in symmetric memory; the NVSwitch reduces them in place
 
     def step(o, d, px):
         with render_hints(image_hw=hint, variant=args.variant):
             out = vol_mod.render_rays(Rays(o, d))
         loss = torch.nn.functional.l1_loss(out.colour, px)
+        if reducer is not None:
+            reducer.zero_grad()  # same 1.95 GB memset as autograd's fresh zero-filled buffers
+            loss.backward()  # the backward kernel accumulates straight into the symmetric buffers
+            reducer.all_reduce()
+            return loss, out
         for p in params:
             p.grad = None
         loss.backward()
@@ -376,7 +388,7 @@ def main():
                 "workload": args.workload, "grid": grid_n, "sh_degree": deg, "image": [side, side], "samples_per_ray": spp,
                 "rays_per_gpu_per_step": n_rays, "ray_order": "flat" if args.flat_order else "image(8x4 tiles)",
                 "perturb": not args.no_perturb, "step": "render_rays fwd + l1_loss + backward (grad zero-fill + fused bwd)"
-                + (" + NCCL all-reduce(grid grad)" if world > 1 else ""),
+                + ((" + NCCL all-reduce(grid grad)" if reducer is None else " + in-switch NVLS all-reduce(grid grad)") if world > 1 else ""),
                 "l2": f"inputs exceed L2: the grid is {grid_n**3 * rec_bytes / 1e6:.0f} MB vs 126 MB",
                 "variant": args.variant,
             },

@@ -174,6 +174,14 @@ R3D_API int r3d_adam_step(float* param, const float* grad, float* exp_avg, float
                   float lr, float beta1, float beta2, float eps, float bias_correction1,
                   float bias_correction2, float grad_scale, void* cuda_stream);
 
+/* In-switch (NVLS) sum all-reduce of a gradient buffer over NVLink/NVSwitch: the exchange between backward() and
+ * optimizer.step() (reference modules/trainers.py:339-341; the reference itself is single-device).  `multicast_ptr` is the
+ * multicast address of a buffer allocated symmetrically on all ranks and bound to one multicast object; rank r reduces and
+ * re-broadcasts slice r (multimem.ld_reduce / multimem.st).  The caller brackets the call with cross-rank barriers on the
+ * same stream.  num_blocks <= 0 picks 2 CTAs per SM. */
+R3D_API int r3d_multimem_all_reduce(void* multicast_ptr, int64_t num_floats, int32_t rank, int32_t world_size,
+                                    int32_t num_blocks, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

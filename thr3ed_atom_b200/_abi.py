@@ -99,6 +99,7 @@ SIGNATURES = {
     "r3d_grid_lookup_fwd": (C.c_int, [C.POINTER(R3dGrid), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "r3d_grid_lookup_bwd": (C.c_int, [C.POINTER(R3dGrid), C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(R3dGridGrad), C.c_void_p]),
     "r3d_mark_touched_voxels": (C.c_int, [C.POINTER(R3dGrid), C.POINTER(R3dRays), C.POINTER(R3dRenderConfig), C.c_void_p, C.c_void_p]),
+    "r3d_multimem_all_reduce": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "r3d_adam_step": (
         C.c_int,
         [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64] + [C.c_float] * 7 + [C.c_void_p],

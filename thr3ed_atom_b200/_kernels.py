@@ -271,3 +271,13 @@ def adam_step(param: Tensor, grad: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, 
             ),
             "r3d_adam_step",
         )
+
+
+def multimem_all_reduce(multicast_ptr: int, num_floats: int, rank: int, world_size: int, device, num_blocks: int = 0) -> None:
+    """Enqueue the in-switch (NVLS) sum all-reduce kernel on the current stream (see ``r3d_multimem_all_reduce``)."""
+    device = torch.device(device)
+    with torch.cuda.device(device):
+        _abi.check(
+            _abi.lib().r3d_multimem_all_reduce(C.c_void_p(multicast_ptr), num_floats, rank, world_size, num_blocks, _stream(device)),
+            "r3d_multimem_all_reduce",
+        )

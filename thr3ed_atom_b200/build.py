@@ -20,7 +20,7 @@ LIB_DIR = PKG_DIR / "_lib"
 LIB_PATH = LIB_DIR / "libr3d_b200.so"
 STAMP = LIB_DIR / "libr3d_b200.stamp"
 
-SOURCES = ["r3d_api.cu", "r3d_render.cu", "r3d_aux.cu"]
+SOURCES = ["r3d_api.cu", "r3d_render.cu", "r3d_aux.cu", "r3d_comm.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",

@@ -97,3 +97,70 @@ def broadcast_grid(module: torch.nn.Module, src: int = 0, group=None) -> None:
         return
     for p in module.parameters():
         dist.broadcast(p.data, src=src, group=group)
+
+
+class NVLSGradientReducer:
+    """Grid gradients kept in symmetric memory and summed across ranks *inside the NVSwitch*.
+
+    NCCL's ring all-reduce moves ``2 (n-1)/n`` x the gradient bytes per GPU and direction.  With NVLink-switch multicast
+    (NVLS) every rank instead pulls the already-reduced sum of its 1/n slice (``multimem.ld_reduce``) and broadcasts it
+    back (``multimem.st``): ~1x the bytes per direction (kernel: ``csrc/r3d_comm.cu``).  For that the gradient has to live
+    in memory that is mapped into one multicast object on all ranks, so this class owns the gradient storage:
+
+        reducer = NVLSGradientReducer(voxel_grid)      # p.grad of every grid parameter now aliases symmetric memory
+        for step in ...:
+            reducer.zero_grad()                        # instead of optimizer.zero_grad() (the buffers must stay)
+            loss = ...; loss.backward()                # the backward kernel accumulates straight into the buffers
+            reducer.all_reduce()                       # barrier -> in-switch reduction -> barrier, on the current stream
+            optimizer.step()
+
+    Raises at construction if symmetric memory / multicast is unavailable (callers fall back to
+    ``all_reduce_grid_gradients``).
+    """
+
+    def __init__(self, module: torch.nn.Module, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from thr3ed_atom_b200.thre3d_reprs import renderers
+
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("NVLSGradientReducer needs an initialised process group")
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world_size = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.params = [p for p in module.parameters() if p.requires_grad]
+        if not self.params:
+            raise RuntimeError("no trainable grid parameters")
+        device = self.params[0].device
+        sizes = [(p.numel() + 3) // 4 * 4 for p in self.params]  # every region stays 16-byte aligned
+        self.total = sum(sizes)
+        self.flat = symm_mem.empty(self.total, dtype=torch.float32, device=device)
+        self.handle = symm_mem.rendezvous(self.flat, self.group.group_name)
+        self.multicast_ptr = int(getattr(self.handle, "multicast_ptr", 0) or 0)
+        if self.multicast_ptr == 0:
+            raise RuntimeError("no NVLS multicast mapping for the gradient buffer on this system")
+        self.flat.zero_()
+        self._registry = renderers._direct_grad_targets
+        self._keys = []
+        offset = 0
+        for p, size in zip(self.params, sizes):
+            view = self.flat[offset : offset + p.numel()].view_as(p)
+            p.grad = view
+            self._registry[p.data_ptr()] = view
+            self._keys.append(p.data_ptr())
+            offset += size
+        self.device = device
+
+    def zero_grad(self) -> None:
+        self.flat.zero_()
+
+    def all_reduce(self, num_blocks: int = 0) -> None:
+        from thr3ed_atom_b200 import _kernels
+
+        self.handle.barrier(channel=0)  # every rank has finished accumulating its gradient
+        _kernels.multimem_all_reduce(self.multicast_ptr, self.total, self.rank, self.world_size, self.device, num_blocks)
+        self.handle.barrier(channel=1)  # every slice has been reduced and broadcast
+
+    def close(self) -> None:
+        for k in self._keys:
+            self._registry.pop(k, None)
+        self._keys = []

@@ -86,6 +86,13 @@ def _current_hints() -> dict:
 # ---------------------------------------------------------------------------------------------
 # autograd binding of the fused kernels
 # ---------------------------------------------------------------------------------------------
+# Optional direct gradient targets: {data_ptr of a grid storage tensor -> buffer of the same shape}.  When a target is
+# registered for a parameter, the backward kernel accumulates straight into it (and autograd receives no gradient for that
+# input) -- used by thr3ed_atom_b200.distributed.NVLSGradientReducer to keep the gradient in symmetric memory, where
+# the NVSwitch can reduce it in place.
+_direct_grad_targets = {}
+
+
 class _FusedSHVoxGridRender(torch.autograd.Function):
     @staticmethod
     def forward(ctx, densities: Tensor, features: Tensor, origins: Tensor, directions: Tensor, grid: VoxelGrid, args: _kernels.RenderArgs):
@@ -108,15 +115,18 @@ class _FusedSHVoxGridRender(torch.autograd.Function):
         origins, directions, colour, depth, acc = ctx.saved_tensors
         desc = ctx.desc
         need_d, need_f = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        grad_d = torch.zeros_like(desc.densities) if need_d else None
-        grad_f = torch.zeros_like(desc.features) if need_f else None
+        direct_d = _direct_grad_targets.get(desc.densities.data_ptr()) if need_d else None
+        direct_f = _direct_grad_targets.get(desc.features.data_ptr()) if need_f else None
+        grad_d = direct_d if direct_d is not None else (torch.zeros_like(desc.densities) if need_d else None)
+        grad_f = direct_f if direct_f is not None else (torch.zeros_like(desc.features) if need_f else None)
         if need_d or need_f:
             _kernels.render_backward(
                 desc, origins, directions, ctx.args, (colour, depth, acc), (g_colour, g_depth, g_acc, g_disparity), grad_d, grad_f,
                 ctx.cache,
             )
         ctx.cache = None  # free the per-sample records as soon as they are consumed
-        return grad_d, grad_f, None, None, None, None
+        # gradients accumulated into a registered target are already where they belong
+        return (None if direct_d is not None else grad_d), (None if direct_f is not None else grad_f), None, None, None, None
 
 
 def sample_cache_limit_bytes() -> int:
