@@ -202,8 +202,10 @@ def main():
     ap.add_argument("--no-perturb", action="store_true")
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--flat-order", action="store_true", help="do not pass the image-shape hint (rays in list order)")
-    ap.add_argument("--reducer", default=os.environ.get("R3D_BENCH_REDUCER", "nccl"), choices=["nccl", "nvls"],
-                    help="N>1: gradient exchange = NCCL all-reduce, or the in-switch multimem kernel (csrc/r3d_comm.cu)")
+    ap.add_argument("--reducer", default=os.environ.get("R3D_BENCH_REDUCER", "auto"), choices=["auto", "nccl", "nvls"],
+                    help="N>1: gradient exchange = NCCL all-reduce, or the in-switch multimem kernel (csrc/r3d_comm.cu). "
+                         "auto = nvls at 8+ ranks (measured 4.04 vs 4.18 ms), nccl below (at 2 ranks the multicast path "
+                         "moves 1.5x the ring's bytes: 4.9 vs 3.3 ms)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -293,10 +295,26 @@ def main():
 
     params = list(voxel_grid.parameters())
     reducer = None
-    if world > 1 and args.reducer == "nvls":
+    want_nvls = args.reducer == "nvls" or (args.reducer == "auto" and world >= 8)
+    if world > 1 and want_nvls:
         from thr3ed_atom_b200.distributed import NVLSGradientReducer
 
-        reducer = NVLSGradientReducer(voxel_grid)  # gradients live in symmetric memory; the NVSwitch reduces them in place
+        # gradients live in symmetric memory; the NVSwitch reduces them in place.  Every rank must take the same branch,
+        # so a failure anywhere (no multicast support) sends all ranks to NCCL.
+        ok = torch.ones(1, device=device)
+        try:
+            reducer = NVLSGradientReducer(voxel_grid)
+        except Exception as e:  # noqa: BLE001
+            if args.reducer == "nvls":
+                raise
+            ok.zero_()
+            print(f"[bench] rank {rank}: NVLS reducer unavailable ({e!r}); using NCCL", file=sys.stderr)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok.item()) == 0.0 and reducer is not None:
+            reducer.close()
+            for p in voxel_grid.parameters():
+                p.grad = None
+            reducer = None
 
     def step(o, d, px):
         with render_hints(image_hw=hint, variant=args.variant):
