@@ -11,6 +11,9 @@ reference modules/trainers.py:339-341).  Grid parameters are replicated on every
     loss.backward()
     all_reduce_grid_gradients(vol_mod.thre3d_repr)    # NCCL over NVLink / NVSwitch
     optimizer.step()
+
+``NVLSGradientReducer`` is the second implementation of the same exchange: the gradient lives in symmetric memory and is
+summed inside the NVSwitch by this repo's own multimem kernel (``csrc/r3d_comm.cu``).
 """
 from __future__ import annotations
 
