@@ -90,6 +90,36 @@ def main():
                                   "ms_per_step": ms, "rays_per_s": len(rays) / (ms * 1e-3), "unique_voxels_touched": touched,
                                   "algorithmic_bytes_step": nbytes, "achieved_gbs": nbytes / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": nbytes / (ms * 1e-3) / 1e9 / peak,
                                   "max_memory_allocated_gb": torch.cuda.max_memory_allocated() / 1e9}
+    if "train" in which:
+        # the reference trainer's batch (modules/trainers.py:278-303): rays of 8 cached views pooled, a random subset of
+        # 32768 drawn with randperm -> incoherent rays in list order; and the same rays sorted back into view/pixel order
+        grid, cfg, intr, pose = make(256, 2, 400, 256, dev)
+        vol_mod = VolumetricModel(grid, render_sh_voxel_grid, cfg, device=dev)
+        pooled = []
+        for k in range(8):
+            rot, trans = spherical_pose(45.0 * k, 60.0, HOTDOG_RADIUS)
+            pooled.append(flatten_rays(cast_rays(intr, CameraPose(rot, trans), device=dev)))
+        o = torch.cat([r.origins for r in pooled])
+        d = torch.cat([r.directions for r in pooled])
+        perm = torch.randperm(o.shape[0], device=dev)[:32768]
+        params = list(grid.parameters())
+        from thr3ed_atom_b200.rendering.volumetric.render_interface import Rays
+
+        for label, sel in (("random order (as the trainer passes them)", perm), ("same rays sorted by view and pixel", perm.sort().values)):
+            rays = Rays(o[sel].contiguous(), d[sel].contiguous())
+            pixels = torch.rand((len(rays), 3), device=dev)
+
+            def step():
+                out_ = vol_mod.render_rays(rays)
+                loss = torch.nn.functional.l1_loss(out_.colour, pixels)
+                for p in params:
+                    p.grad = None
+                loss.backward()
+
+            ms = events(step, iters=10)
+            out.setdefault("train_batch_32768_rays", []).append(
+                {"workload": "256^3 deg-2, 32768 rays drawn from 8 pooled 400x400 views, 256 spp, fwd + bwd (incl. 1.95 GB gradient zero-fill)",
+                 "ray_order": label, "ms_per_step": ms, "rays_per_s": len(rays) / (ms * 1e-3)})
     print(json.dumps(out, indent=1))
 
 

@@ -496,3 +496,40 @@ def test_cooperative_and_per_ray_kernels_agree(name, cuda_device, monkeypatch):
         assert torch.equal(res[0], ref[0]) and torch.equal(res[1], ref[1]), label
         assert rel_l2(res[2].cpu().numpy(), ref[2].cpu().numpy()) < 1e-5, label
         assert rel_l2(res[3].cpu().numpy(), ref[3].cpu().numpy()) < 1e-5, label
+
+
+@pytest.mark.parametrize("num_rays", [1, 31, 33, 129, 1000])
+def test_ragged_batch_sizes(num_rays, cuda_device):
+    """Batches that do not fill a warp / a CTA, incl. a single ray (the reference's .squeeze() breaks at one point,
+    voxels.py:305; the kernels have no such restriction)."""
+    case = CASES["deg2_16cube"]
+    inp = build_inputs(case)
+    idx = np.linspace(0, inp["origins"].shape[0] - 1, num_rays).astype(np.int64)
+    sub = {k: (v[idx] if k in ("origins", "directions", "grad_colour") else v) for k, v in inp.items()}
+    want = run_numpy_f64(case, sub)
+    got = run_cuda_case(case, sub, cuda_device)
+    assert_outputs_close(got, want, atol=1e-5, rtol_depth=1e-5, what=f"n={num_rays}")
+    assert rel_l2(got["grad_features"], want["grad_features"]) < 5e-5
+    assert rel_l2(got["grad_densities"], want["grad_densities"]) < 5e-5
+
+
+def test_many_samples_per_ray_and_non_contiguous_ray_views(cuda_device):
+    """1024 samples per ray (the reference's render default, renderers.py:44) on rays given as strided views."""
+    from thr3ed_atom_b200.rendering.volumetric.render_interface import Rays
+    from thr3ed_atom_b200.thre3d_reprs.renderers import render_sh_voxel_grid
+
+    case = dataclasses.replace(CASES["deg2_16cube"], num_samples=1024, name="s1024")
+    inp = build_inputs(case)
+    keep = np.arange(0, inp["origins"].shape[0], 7)
+    sub = {k: (v[keep] if k in ("origins", "directions", "grad_colour") else v) for k, v in inp.items()}
+    want = run_numpy_f64(case, sub)
+    grid = make_cuda_grid(case, inp, cuda_device)
+    both = torch.from_numpy(np.concatenate([inp["origins"], inp["directions"]], -1)).to(cuda_device)  # [N, 6]
+    rays = Rays(both[::7, :3], both[::7, 3:])  # non-contiguous views
+    assert not rays.origins.is_contiguous()
+    out = render_sh_voxel_grid(grid, rays, make_cuda_config(case))
+    (out.colour * torch.from_numpy(sub["grad_colour"]).to(cuda_device)).sum().backward()
+    got = {"colour": out.colour.detach().cpu().numpy(), "depth": out.depth.detach().cpu().numpy(),
+           "acc": out.extra["accumulated_weight"].detach().cpu().numpy(), "disparity": out.extra["disparity"].detach().cpu().numpy()}
+    assert_outputs_close(got, want, atol=1e-5, rtol_depth=1e-5, what="s1024")
+    assert rel_l2(grid.feature_storage.grad[..., :27].cpu().numpy(), want["grad_features"]) < 5e-5

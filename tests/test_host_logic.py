@@ -323,3 +323,22 @@ def test_shard_bounds_cover_everything_once():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [e - s for s, e in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_reference_import_paths_resolve_through_the_compat_shim(monkeypatch):
+    import importlib
+    import sys
+    from pathlib import Path
+
+    monkeypatch.syspath_prepend(str(Path(__file__).resolve().parent.parent / "compat"))
+    for name in [m for m in sys.modules if m == "thre3d_atom" or m.startswith("thre3d_atom.")]:
+        monkeypatch.delitem(sys.modules, name)
+    from thre3d_atom.modules.volumetric_model import VolumetricModel as VM  # noqa: E402
+    from thre3d_atom.rendering.volumetric.render_interface import Rays as R  # noqa: E402
+    from thre3d_atom.thre3d_reprs.renderers import SHVoxGridRenderConfig as C, render_sh_voxel_grid as f  # noqa: E402
+    from thre3d_atom.thre3d_reprs.voxels import VoxelGrid as VG  # noqa: E402
+    from thre3d_atom.utils.imaging_utils import CameraBounds as CB  # noqa: E402
+
+    assert f is render_sh_voxel_grid and C is SHVoxGridRenderConfig and VG is VoxelGrid and VM is VolumetricModel
+    assert R is Rays and CB is CameraBounds
+    assert importlib.import_module("thre3d_atom.thre3d_reprs.constants").u_FEATURES == "_features"

@@ -1,15 +1,16 @@
-"""Model facade around (representation, render procedure, render config).
+"""Model facade: a 3-D representation + the procedure that renders it + that procedure's configuration.
 
-API mirror of the reference's ``thre3d_atom/modules/volumetric_model.py`` (``VolumetricModel`` :30-174,
-``create_volumetric_model_from_saved_model`` :177-197).  Control flow only -- the work happens in the
-render procedure.  Two deliberate differences, both invisible in results:
+Keeps the public surface of the reference's ``VolumetricModel`` (thre3d_atom/modules/volumetric_model.py:30-174) and of
+``create_volumetric_model_from_saved_model`` (:177-197): callers hold one of these, call ``render_rays`` while training
+and ``render`` for whole images, and checkpoint through ``get_save_info``.  It is control flow only -- the work happens in
+the render procedure.  Two deliberate differences, both invisible in results:
 
-* ``render`` recognises the fused SH voxel-grid procedure and renders the whole image in one launch
-  with in-kernel ray generation; ``parallel_rays_chunk_size`` / ``parallel_points_chunk_size`` exist in
-  the reference only because it materialises ``[rays * samples, F + 1]`` tensors, so they are accepted
-  and not needed.  Any other procedure takes the reference's chunked loop.
-* checkpoints are loaded with ``weights_only=False`` (they hold pickled callables and NamedTuples by
-  design, reference volumetric_model.py:86-96; torch >= 2.6 refuses them by default).
+* ``render`` recognises the fused SH voxel-grid procedure and renders the whole image in ONE launch with in-kernel ray
+  generation.  The reference chunks rays (``parallel_rays_chunk_size``) and points (``parallel_points_chunk_size``) only
+  because its op-by-op pipeline materialises ``[rays * samples, F + 1]`` tensors; both arguments are accepted and are
+  only used for procedures other than the fused one.
+* checkpoints are read with ``weights_only=False``: they hold pickled callables and NamedTuples by design
+  (reference volumetric_model.py:86-96) and torch >= 2.6 refuses those by default.
 """
 from __future__ import annotations
 
@@ -22,20 +23,8 @@ import torch
 from torch.nn import Module
 
 from thr3ed_atom_b200.rendering.volumetric.render_interface import Rays, RenderOut
-from thr3ed_atom_b200.rendering.volumetric.utils.misc import (
-    cast_rays,
-    collate_rendered_output,
-    flatten_rays,
-    reshape_rendered_output,
-)
-from thr3ed_atom_b200.thre3d_reprs.constants import (
-    CONFIG_DICT,
-    RENDER_CONFIG,
-    RENDER_CONFIG_TYPE,
-    RENDER_PROCEDURE,
-    STATE_DICT,
-    THRE3D_REPR,
-)
+from thr3ed_atom_b200.rendering.volumetric.utils import misc as ray_utils
+from thr3ed_atom_b200.thre3d_reprs import constants as ckpt
 from thr3ed_atom_b200.thre3d_reprs.renderers import (
     RenderConfig,
     RenderProcedure,
@@ -45,6 +34,22 @@ from thr3ed_atom_b200.thre3d_reprs.renderers import (
 from thr3ed_atom_b200.utils.constants import EXTRA_INFO
 from thr3ed_atom_b200.utils.imaging_utils import CameraIntrinsics, CameraPose
 
+_DEFAULT_DEVICE = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+_CPU = torch.device("cpu")
+
+
+def _with_overrides(render_config: RenderConfig, overrides: Dict[str, Any]) -> RenderConfig:
+    """A deep copy of ``render_config`` with some fields replaced; naming a field it does not have is an error."""
+    if not overrides:
+        return copy.deepcopy(render_config)
+    patched = copy.deepcopy(render_config)
+    for name in overrides:
+        if not hasattr(patched, name):
+            raise ValueError(f"Unknown render configuration field {name} requested for overriding :(")
+    for name, value in overrides.items():
+        setattr(patched, name, value)
+    return patched
+
 
 class VolumetricModel:
     def __init__(
@@ -52,61 +57,33 @@ class VolumetricModel:
         thre3d_repr: Module,
         render_procedure: RenderProcedure,
         render_config: RenderConfig,
-        device: torch.device = torch.device("cuda" if torch.cuda.is_available() else "cpu"),
+        device: torch.device = _DEFAULT_DEVICE,
     ) -> None:
-        self._thre3d_repr = thre3d_repr.to(device)
-        self._render_procedure = render_procedure
-        self._render_config = render_config
         self._device = device
+        self._render_config = render_config
+        self._render_procedure = render_procedure
+        self._thre3d_repr = thre3d_repr.to(device)
+
+    # ---- read access to the three parts (the representation can be swapped, e.g. after a grid up-scale) ----
+    device = property(lambda self: self._device)
+    render_config = property(lambda self: self._render_config)
+    render_procedure = property(lambda self: self._render_procedure)
 
     @property
     def thre3d_repr(self) -> Module:
         return self._thre3d_repr
 
     @thre3d_repr.setter
-    def thre3d_repr(self, thre3d_repr: Module) -> None:
-        self._thre3d_repr = thre3d_repr
+    def thre3d_repr(self, new_repr: Module) -> None:
+        self._thre3d_repr = new_repr
 
-    @property
-    def render_procedure(self) -> RenderProcedure:
-        return self._render_procedure
+    _update_render_config = staticmethod(_with_overrides)
 
-    @property
-    def render_config(self) -> RenderConfig:
-        return self._render_config
-
-    @property
-    def device(self) -> torch.device:
-        return self._device
-
-    @staticmethod
-    def _update_render_config(render_config: RenderConfig, update_dict: Dict[str, Any]) -> RenderConfig:
-        """copy of ``render_config`` with the given fields overridden; unknown fields are an error"""
-        updated = copy.deepcopy(render_config)
-        for field, value in update_dict.items():
-            if not hasattr(updated, field):
-                raise ValueError(f"Unknown render configuration field {field} requested for overriding :(")
-            setattr(updated, field, value)
-        return updated
-
-    def get_save_info(self, extra_info: Optional[Dict[str, Any]] = None) -> Dict[str, Any]:
-        save_info = {
-            THRE3D_REPR: {
-                STATE_DICT: self._thre3d_repr.state_dict(),
-                CONFIG_DICT: self._thre3d_repr.get_save_config_dict(),
-            },
-            RENDER_PROCEDURE: self._render_procedure,
-            RENDER_CONFIG_TYPE: type(self._render_config),
-            RENDER_CONFIG: dataclasses.asdict(self._render_config),
-        }
-        if extra_info is not None:
-            save_info[EXTRA_INFO] = extra_info
-        return save_info
-
+    # ---- rendering ----
     def render_rays(self, rays: Rays, parallel_points_chunk_size: Optional[int] = None, **kwargs) -> RenderOut:
-        """differentiable render of a flat batch of rays; ``kwargs`` override render-config fields for this call"""
-        render_config = self._update_render_config(self._render_config, kwargs)
-        return self._render_procedure(self._thre3d_repr, rays, render_config, parallel_points_chunk_size)
+        """Differentiable render of a flat ray batch; ``kwargs`` override render-config fields for this call only."""
+        call_config = _with_overrides(self._render_config, kwargs)
+        return self._render_procedure(self._thre3d_repr, rays, call_config, parallel_points_chunk_size)
 
     def render(
         self,
@@ -118,36 +95,56 @@ class VolumetricModel:
         verbose: bool = False,
         **kwargs,
     ) -> RenderOut:
-        """no-grad render of a full ``[H, W]`` image for a camera; ``kwargs`` override render-config fields"""
+        """Gradient-free render of the full ``[H, W]`` image seen by a camera; ``kwargs`` override render-config fields.
+        ``gpu_render=False`` returns CPU tensors."""
         if self._render_procedure is render_sh_voxel_grid:
-            render_config = self._update_render_config(self._render_config, kwargs)
-            flat = render_sh_voxel_grid_camera(self._thre3d_repr, camera_intrinsics, camera_pose, render_config)
+            image = render_sh_voxel_grid_camera(self._thre3d_repr, camera_intrinsics, camera_pose, _with_overrides(self._render_config, kwargs))
         else:
-            flat_rays = flatten_rays(cast_rays(camera_intrinsics, camera_pose, device=self._device))
-            chunk = len(flat_rays) if parallel_rays_chunk_size is None else parallel_rays_chunk_size
-            chunks = []
-            with torch.no_grad():
-                for start in range(0, len(flat_rays), chunk):
-                    out = self.render_rays(flat_rays[start : start + chunk], parallel_points_chunk_size, **kwargs)
-                    chunks.append(out if gpu_render else out.to(torch.device("cpu")))
-            flat = collate_rendered_output(chunks)
+            image = self._render_in_ray_chunks(camera_pose, camera_intrinsics, parallel_rays_chunk_size, parallel_points_chunk_size, kwargs)
         if not gpu_render:
-            flat = flat.to(torch.device("cpu"))
-        return reshape_rendered_output(flat, camera_intrinsics=camera_intrinsics)
+            image = image.to(_CPU)
+        return ray_utils.reshape_rendered_output(image, camera_intrinsics=camera_intrinsics)
+
+    def _render_in_ray_chunks(self, camera_pose, camera_intrinsics, rays_per_chunk, points_per_chunk, overrides) -> RenderOut:
+        """Generic path for user-supplied procedures: cast all rays, render them chunk by chunk without autograd."""
+        all_rays = ray_utils.flatten_rays(ray_utils.cast_rays(camera_intrinsics, camera_pose, device=self._device))
+        total = len(all_rays)
+        step = total if rays_per_chunk is None else rays_per_chunk
+        pieces = []
+        with torch.no_grad():
+            for begin in range(0, total, step):
+                pieces.append(self.render_rays(all_rays[begin : begin + step], points_per_chunk, **overrides))
+        return ray_utils.collate_rendered_output(pieces)
+
+    # ---- checkpoints ----
+    def get_save_info(self, extra_info: Optional[Dict[str, Any]] = None) -> Dict[str, Any]:
+        """Everything needed to rebuild this model: representation state + config, the procedure, the config type and values."""
+        payload = {
+            ckpt.THRE3D_REPR: {
+                ckpt.STATE_DICT: self._thre3d_repr.state_dict(),
+                ckpt.CONFIG_DICT: self._thre3d_repr.get_save_config_dict(),
+            },
+            ckpt.RENDER_PROCEDURE: self._render_procedure,
+            ckpt.RENDER_CONFIG_TYPE: type(self._render_config),
+            ckpt.RENDER_CONFIG: dataclasses.asdict(self._render_config),
+        }
+        if extra_info is not None:
+            payload[EXTRA_INFO] = extra_info
+        return payload
 
 
 def create_volumetric_model_from_saved_model(
     model_path: Path,
     thre3d_repr_creator: Callable[[Dict[str, Any]], Module],
-    device: torch.device = torch.device("cpu"),
+    device: torch.device = _CPU,
 ) -> Tuple[VolumetricModel, Dict[str, Any]]:
-    model_data = torch.load(model_path, weights_only=False)
-    thre3d_repr = thre3d_repr_creator(model_data)
-    render_config = model_data[RENDER_CONFIG_TYPE](**model_data[RENDER_CONFIG])
-    vol_mod = VolumetricModel(
-        thre3d_repr=thre3d_repr,
-        render_procedure=model_data[RENDER_PROCEDURE],
-        render_config=render_config,
+    """Inverse of ``torch.save(vol_mod.get_save_info(extra))``: returns the rebuilt model and the saved extra info."""
+    saved = torch.load(model_path, weights_only=False)
+    config = saved[ckpt.RENDER_CONFIG_TYPE](**saved[ckpt.RENDER_CONFIG])
+    model = VolumetricModel(
+        thre3d_repr=thre3d_repr_creator(saved),
+        render_procedure=saved[ckpt.RENDER_PROCEDURE],
+        render_config=config,
         device=device,
     )
-    return vol_mod, model_data[EXTRA_INFO]
+    return model, saved[EXTRA_INFO]
