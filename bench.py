@@ -52,6 +52,8 @@ WORKLOADS = {
     "c3_256cube_deg2_800px_256spp": (256, 2, 800, 256),
     "c2_128cube_deg2_400px_128spp": (128, 2, 400, 128),
     "c1_32cube_deg0_64px_32spp": (32, 0, 64, 32),
+    # BASELINE.json configs[4] (8-GPU stress shape; not the bench line): --workload c5_512cube_deg3_1600px_512spp
+    "c5_512cube_deg3_1600px_512spp": (512, 3, 1600, 512),
 }
 HOTDOG_RADIUS, NEAR, FAR = 4.031128406524658, 1.8, 6.6
 WORLD = (3.0, 3.0, 3.0)
@@ -243,7 +245,14 @@ def main():
 
     grid_n, deg, side, spp = WORKLOADS[args.workload]
     nf = 3 * (deg + 1) ** 2
-    dens, feat = make_grid_values(grid_n, deg)
+    if grid_n**3 * (nf + 1) * 4 > 8 * 2**30:
+        # 512^3 deg 3 is 26 GB per replica: draw it on the device (same U(-1,1) law, same seed on every rank)
+        gdev = torch.Generator(device=device).manual_seed(42)
+        dens = torch.empty((grid_n, grid_n, grid_n, 1), dtype=torch.float32, device=device).uniform_(-1.0, 1.0, generator=gdev)
+        feat = torch.empty((grid_n, grid_n, grid_n, nf), dtype=torch.float32, device=device).uniform_(-1.0, 1.0, generator=gdev)
+        args.no_cpu_baseline = True
+    else:
+        dens, feat = make_grid_values(grid_n, deg)
     voxel_grid = VoxelGrid(
         densities=dens.to(device), features=feat.to(device), voxel_size=VoxelSize(*[w / grid_n for w in WORLD]),
         density_preactivation=torch.nn.Identity(), density_postactivation=torch.nn.ReLU(),
