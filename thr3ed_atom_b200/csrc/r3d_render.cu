@@ -1,27 +1,40 @@
-// r3d_render.cu -- fused per-ray forward and backward kernels of the SH-voxel-grid renderer (sm_100a).
+// r3d_render.cu -- fused forward and backward kernels of the SH-voxel-grid renderer (sm_100a).
 //
-// One thread owns one ray and marches it front to back.  Per sample it
+// Kernels in this file
+//   render_fwd_coop_kernel   forward, default: per-ray maths + warp-cooperative gather through shared memory
+//   render_fwd_kernel        forward, one thread per ray end to end (band-0 "diffuse" renders, unpadded layouts, A/B)
+//   render_bwd_coop_kernel   backward, default: per-ray maths + warp-cooperative, cell-merged scatter
+//   render_bwd_kernel        backward, one thread per ray end to end (A/B)
+//   mark_touched_kernel      measurement helper (unique voxels referenced by a batch)
+//
+// Common structure.  One thread owns one ray and marches it front to back.  Per sample it
 //   1. forms the sample position exactly as the reference does (sample.py:54-67),
 //   2. applies the strict inside-AABB test (voxels.py:252-274 / process.py:80-84),
 //   3. gathers the 8 corner densities (a [W][D][H] fp32 volume: 4 B/voxel, L2 resident up to 256^3+),
 //      interpolates, scales and activates them (voxels.py:292-309),
-//   4. ONLY IF the sample's density is non-zero gathers the 8 corner SH records with 128-bit loads,
-//      contracts each with the ray's SH basis (the contraction is linear, so it commutes with the
-//      trilinear weights: 3 accumulators instead of 3*(deg+1)^2), applies sigmoid and composites
+//   4. ONLY IF the sample's density is non-zero needs the 8 corner SH records; each record is contracted with
+//      the ray's SH basis first (the contraction is linear, so it commutes with the trilinear weights:
+//      3 accumulators instead of 3*(deg+1)^2), then sigmoid and compositing
 //      (spherical_harmonics.py:86-116, accumulate.py:43-88).
 // A sample with sigma == 0 has alpha == 0 exactly, hence weight 0 and no effect on colour, depth,
 // acc or the transmittance, and (ReLU' = 0) no gradient: skipping its feature traffic is exact.
 // Likewise a ray whose transmittance reached exactly 0 can stop.
 //
-// The backward kernel re-marches the ray (no per-sample tensors are saved), rebuilding alpha/T/raw,
-// and uses the forward's outputs for the suffix sums:
+// The backward kernels re-march the ray (nothing of size N*S is saved except the optional sample cache of
+// (sigmoid(raw), sigma) records written by the forward), rebuild alpha/T, and use the forward's outputs for the
+// suffix sums:
 //   dL/dsigma_i = delta_i * ( T_{i+1} q_i - sum_{j>i} w_j q_j ),   sum_{j>i} = Total - prefix_i
 //   q_i = g_c . sigmoid(raw_i) + g_d z_i + g_a,  Total = g_c . C_fg + g_d depth + g_a acc
 // (SURVEY.md A.6).  Gradients are scattered with 128-bit vector reductions (red.global.add.v4.f32).
+//
+// The cooperative kernels exist because of what the profiles showed: the path is bound by the
+// L1 data pipe -- one wavefront per distinct 128-byte line per request -- not by HBM; they make consecutive lanes
+// cover consecutive bytes of ONE voxel record and merge samples that share an interpolation cell.
 #include "r3d_host.h"
 
 // resident CTAs per SM the cooperative kernels are compiled for (register budget = 65536 / (128 * blocks)).
-// Measured at c3 on the B200: backward 7.95 ms at 4, 7.45 ms at 5 (96 registers, ~40 bytes of spill); forward unchanged.
+// Measured at c3 on the B200: backward 7.95 ms at 4 CTAs/SM, 7.45 ms at 5 (96 registers, a few bytes of spill);
+// forward unchanged between 4 and 5.
 #ifndef R3D_FWD_BLOCKS
 #define R3D_FWD_BLOCKS 4
 #endif
@@ -369,7 +382,7 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_FWD_BLOCKS) render_fwd
     int vox[8];
     float sigma = 0.f, zn = 0.f;
     bool last = false;
-    int key = -1;
+    unsigned long long key = 0ull;  // 64-bit: voxel offset (up to 2^31) + the low corner's validity pattern
     const bool mine = marching && i >= s.i_lo && i <= s.i_hi;
     if (mine) {
       if (!have_z) z = s.dg.at(i), have_z = true;
@@ -391,7 +404,7 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_FWD_BLOCKS) render_fwd
             wc[k] = cell.wx[ix] * cell.wy[iy] * cell.wz[iz];
             vox[k] = cell.ox[ix] + cell.oy[iy] + cell.oz[iz];
           }
-          key = vox[0] ^ ((cell.wx[0] != 0.f) << 28) ^ ((cell.wy[0] != 0.f) << 29) ^ ((cell.wz[0] != 0.f) << 30);
+          key = (unsigned long long)(unsigned)vox[0] | ((unsigned long long)((cell.wx[0] != 0.f) | ((cell.wy[0] != 0.f) << 1) | ((cell.wz[0] != 0.f) << 2)) << 32);
         }
       }
     }
@@ -718,7 +731,7 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_BWD_BLOCKS) render_bwd
     float wc[8];
     int vox[8];
     float draw[3] = {0.f, 0.f, 0.f}, dpre = 0.f;
-    int key = -1;
+    unsigned long long key = 0ull;  // 64-bit: voxel offset (up to 2^31) + the low corner's validity pattern
     if (alive && i >= s.i_lo && i <= s.i_hi) {
       if (!have_z) z = s.dg.at(i), have_z = true;
       const bool last = (i == c.S - 1);
@@ -769,7 +782,7 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_BWD_BLOCKS) render_bwd
             }
             // the clamped offsets of the low corner identify the cell unless it is clamped at the border; fold the
             // validity pattern in so that border cells with different zero-padding never merge
-            key = vox[0] ^ ((cell.wx[0] != 0.f) << 28) ^ ((cell.wy[0] != 0.f) << 29) ^ ((cell.wz[0] != 0.f) << 30);
+            key = (unsigned long long)(unsigned)vox[0] | ((unsigned long long)((cell.wx[0] != 0.f) | ((cell.wy[0] != 0.f) << 1) | ((cell.wz[0] != 0.f) << 2)) << 32);
           }
           T = Tn;
           if (T == 0.0f) alive = false;  // every later weight is exactly 0
