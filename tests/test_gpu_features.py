@@ -153,7 +153,9 @@ def test_point_lookup_matches_reference(name, cuda_device):
 @pytest.mark.parametrize("name", ["deg2_16cube", "c1_32cube_deg0"])
 def test_unpadded_reference_layout_gives_the_same_result(name, cuda_device):
     """The C ABI accepts any record stride: whole 16-byte vectors (what VoxelGrid stores), whole 32-byte sectors
-    (256-bit loads in the per-ray kernels) and the reference's unpadded layout (scalar loads).  All give the same result."""
+    (256-bit loads in the per-ray kernels) and the reference's unpadded layout (scalar loads).  All give the same result
+    (the padded layouts take the lane-group forward, which sums in another order than the per-ray kernel the unpadded
+    layout takes: equal to fp32 rounding, not bit for bit)."""
     from thr3ed_atom_b200 import _kernels
     from thr3ed_atom_b200.thre3d_reprs.renderers import make_render_args
 
@@ -180,7 +182,7 @@ def test_unpadded_reference_layout_gives_the_same_result(name, cuda_device):
     (out_p, gp_d, gp_f) = results[0]
     for out_o, go_d, go_f in results[1:]:
         for a, b in zip(out_p[:3], out_o[:3]):
-            assert torch.equal(a, b)
+            assert ((a - b).abs() <= 2e-6 * b.abs().clamp(min=1.0)).all()
         assert rel_l2(gp_f[..., :nf].cpu().numpy(), go_f[..., :nf].cpu().numpy()) < 1e-5
         assert rel_l2(gp_d.cpu().numpy(), go_d.cpu().numpy()) < 1e-5
         assert not bool(go_f[..., nf:].any())
@@ -469,16 +471,18 @@ def test_config3_shape_properties(cuda_device):
 
 @pytest.mark.parametrize("name", ["deg2_16cube", "deg3_abs", "deg1_aniso_softplus", "c1_32cube_deg0", "deg2_jitter_optimized"])
 def test_cooperative_and_per_ray_kernels_agree(name, cuda_device, monkeypatch):
-    """The warp-cooperative kernels (default) against the thread-per-ray kernels (variant 3), with and without the
-    forward's sample cache: same per-ray arithmetic => bit-identical images, gradients equal up to summation order."""
+    """The warp-cooperative kernels against the thread-per-ray kernels (variant 3), with and without the forward's sample
+    cache.  The staged forwards (variants 8, 4) do the per-ray arithmetic of the per-ray kernel => bit-identical images;
+    the default lane-group forward sums the 8 corners and the SH terms in another order => equal to fp32 rounding.
+    Gradients are equal up to summation order."""
     from thr3ed_atom_b200.thre3d_reprs.renderers import render_hints, render_sh_voxel_grid
 
     case = CASES[name]
     inp = build_inputs(case)
     gc = torch.from_numpy(inp["grad_colour"]).to(cuda_device)
     results = {}
-    for label, variant, cache_limit in (("coop+cache", 0, None), ("per-ray+cache", 3, None), ("coop", 0, "0"), ("per-ray", 3, "0"),
-                                        ("coop, TMA staging", 4, None)):
+    for label, variant, cache_limit in (("group+cache", 0, None), ("per-ray+cache", 3, None), ("group", 0, "0"), ("per-ray", 3, "0"),
+                                        ("staged+cache", 8, None), ("staged", 8, "0"), ("staged, TMA", 4, None)):
         if cache_limit is None:
             monkeypatch.delenv("R3D_SAMPLE_CACHE_MAX_BYTES", raising=False)
         else:
@@ -493,7 +497,11 @@ def test_cooperative_and_per_ray_kernels_agree(name, cuda_device, monkeypatch):
         results[label] = (out.colour.detach().clone(), out.depth.detach().clone(), grid.densities.grad.clone(), grid.feature_storage.grad.clone())
     ref = results["per-ray"]
     for label, res in results.items():
-        assert torch.equal(res[0], ref[0]) and torch.equal(res[1], ref[1]), label
+        if label.startswith("group"):
+            assert (res[0] - ref[0]).abs().max().item() < 2e-6, label
+            assert ((res[1] - ref[1]).abs() <= 2e-6 * ref[1].abs().clamp(min=1.0)).all(), label
+        else:
+            assert torch.equal(res[0], ref[0]) and torch.equal(res[1], ref[1]), label
         assert rel_l2(res[2].cpu().numpy(), ref[2].cpu().numpy()) < 1e-5, label
         assert rel_l2(res[3].cpu().numpy(), ref[3].cpu().numpy()) < 1e-5, label
 

@@ -7,10 +7,12 @@ object has not been built (``python -m thr3ed_atom_b200.build``), and every entr
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 from typing import Optional
 
-LIB_PATH = Path(__file__).resolve().parent / "_lib" / "libr3d_b200.so"
+# $R3D_LIB_PATH selects another build of the same library (tuning experiments: other -D flags); default = the in-tree build
+LIB_PATH = Path(os.environ.get("R3D_LIB_PATH") or (Path(__file__).resolve().parent / "_lib" / "libr3d_b200.so"))
 ABI_VERSION = 2
 
 # enums of r3d_b200.h

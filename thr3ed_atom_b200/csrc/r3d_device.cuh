@@ -164,6 +164,29 @@ struct DepthGen {
   }
 };
 
+// Depths of CONSECUTIVE samples j, j+1, j+2, ...: same values as DepthGen::at (bit for bit), but the two unjittered
+// depths a stratum shares with its predecessor are carried in registers, so a step evaluates one base() instead of three.
+struct DepthMarch {
+  float bm, bc;  // base(j - 1), base(j) of the next sample j to be produced
+  __device__ __forceinline__ void start(const DepthGen& dg, int j) {
+    bc = dg.base(j);
+    bm = (dg.perturb && j > 0) ? dg.base(j - 1) : bc;
+  }
+  __device__ __forceinline__ float next(const DepthGen& dg, int j) {
+    const float b = bc;
+    const float bn = (j < dg.S - 1) ? dg.base(j + 1) : b;
+    float z = b;
+    if (dg.perturb) {
+      const float lower = (j > 0) ? 0.5f * __fadd_rn(b, bm) : b;
+      const float upper = (j < dg.S - 1) ? 0.5f * __fadd_rn(bn, b) : b;
+      const float u = dg.jit ? __ldg(dg.jit + j) : jitter_u(dg.key, j);
+      z = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), u));
+    }
+    bm = b, bc = bn;
+    return z;
+  }
+};
+
 // Per-ray (near, far) of `optimized_sampling` -- the reference's slab test with all its quirks
 // (rendering/volumetric/sample.py:71-183): denominators d + 1e-10, the miss test of an axis uses the
 // interval accumulated over the previous axes, misses fall back to the camera bounds, clip at 0.
@@ -262,6 +285,26 @@ __device__ __forceinline__ void make_cell(const GridP& g, float px, float py, fl
   axis_cell(pz, g.ns[2], g.nb[2], g.H, 1, c.oz, c.wz);
 }
 
+// Same cell for a point that passed inside_aabb: n is then within a rounding error of [-1, 1], so the continuous index
+// lies in (-0.5 - eps, dim - 0.5 + eps) and the float-side range clamp of axis_cell is the identity (bit-identical
+// weights and offsets); the integer clamps stay, they keep every address in range whatever the caller passed.
+__device__ __forceinline__ void axis_cell_inside(float p, float ns, float nb, int dim, int mul, int (&off)[2], float (&w)[2]) {
+  const float n = __fadd_rn(__fmul_rn(p, ns), nb);
+  const float gi = ((n + 1.0f) * (float)dim - 1.0f) * 0.5f;
+  const float fl = floorf(gi);
+  const int i0 = (int)fl;
+  w[0] = ((unsigned)i0 < (unsigned)dim) ? (fl + 1.0f) - gi : 0.0f;
+  w[1] = ((unsigned)(i0 + 1) < (unsigned)dim) ? gi - fl : 0.0f;
+  off[0] = min(max(i0, 0), dim - 1) * mul;
+  off[1] = min(max(i0 + 1, 0), dim - 1) * mul;
+}
+
+__device__ __forceinline__ void make_cell_inside(const GridP& g, float px, float py, float pz, Cell& c) {
+  axis_cell_inside(px, g.ns[0], g.nb[0], g.W, g.D * g.H, c.ox, c.wx);
+  axis_cell_inside(py, g.ns[1], g.nb[1], g.D, g.H, c.oy, c.wy);
+  axis_cell_inside(pz, g.ns[2], g.nb[2], g.H, 1, c.oz, c.wz);
+}
+
 __device__ __forceinline__ bool inside_aabb(const GridP& g, float px, float py, float pz) {
   // strict inequalities, voxels.py:252-274
   return (px > g.lo[0]) && (px < g.hi[0]) && (py > g.lo[1]) && (py < g.hi[1]) && (pz > g.lo[2]) && (pz < g.hi[2]);
@@ -334,6 +377,26 @@ __device__ __forceinline__ void sh_basis(float x, float y, float z, float (&Y)[(
   }
 }
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+// Transcendentals of the compositing stage.  Default: the SFU forms (ex2.approx behind __expf, rcp.approx behind
+// __fdividef) -- 2 + floor(|1.44 x|) ulp on exp, i.e. ~2e-7 relative for the sigma*delta and raw-radiance ranges that
+// matter, against a stated colour tolerance of 1e-5; ~6 instructions instead of ~25 per sample.  -DR3D_PRECISE_MATH=1
+// selects expf and IEEE division.
+#ifndef R3D_PRECISE_MATH
+#define R3D_PRECISE_MATH 0
+#endif
+__device__ __forceinline__ float exp_neg(float x) {  // exp(-x)
+#if R3D_PRECISE_MATH
+  return expf(-x);
+#else
+  return __expf(-x);
+#endif
+}
+__device__ __forceinline__ float sigmoidf_(float x) {
+#if R3D_PRECISE_MATH
+  return 1.0f / (1.0f + expf(-x));
+#else
+  return __fdividef(1.0f, 1.0f + __expf(-x));  // exp -> inf gives 0, exp -> 0 gives 1, like the IEEE form
+#endif
+}
 
 }  // namespace r3d

@@ -226,22 +226,24 @@ __global__ void __launch_bounds__(128) render_fwd_kernel(const GridP g, const Ra
 
   float T = 1.0f, cr = 0.f, cg = 0.f, cb = 0.f, dep = 0.f, acc = 0.f;
   if (s.i_lo <= s.i_hi) {
-    float z = s.dg.at(s.i_lo);
+    DepthMarch dm;
+    dm.start(s.dg, s.i_lo);
+    float z = dm.next(s.dg, s.i_lo);
     for (int i = s.i_lo; i <= s.i_hi; ++i) {
       const bool last = (i == c.S - 1);
-      const float zn = last ? 0.0f : s.dg.at(i + 1);
+      const float zn = last ? 0.0f : dm.next(s.dg, i + 1);
       const float px = __fadd_rn(r.ox, __fmul_rn(r.dx, z));  // sample.py:67
       const float py = __fadd_rn(r.oy, __fmul_rn(r.dy, z));
       const float pz = __fadd_rn(r.oz, __fmul_rn(r.dz, z));
       if (inside_aabb(g, px, py, pz)) {
         Cell cell;
-        make_cell(g, px, py, pz, cell);
+        make_cell_inside(g, px, py, pz, cell);
         float dpost;
         const float sigma = density_post(g.post, density_pre_interp(g, cell), dpost);
         if (sigma != 0.0f) {
           // accumulate.py:49-55, :24-28
           const float delta = last ? __fmul_rn(kInfinity, s.dnorm) : __fmul_rn(__fsub_rn(zn, z), s.dnorm);
-          const float alpha = 1.0f - expf(-(sigma * delta));
+          const float alpha = 1.0f - exp_neg(sigma * delta);
           const float w = alpha * T;
           float rr, rg, rb;
           gather_radiance<DEG, VEC>(g, cell, Y, diffuse, rr, rg, rb);
@@ -375,6 +377,8 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_FWD_BLOCKS) render_fwd
   float T = 1.0f, cr = 0.f, cg = 0.f, cb = 0.f, dep = 0.f, acc = 0.f;
   float z = 0.f;
   bool have_z = false;
+  DepthMarch dm;
+  dm.bm = dm.bc = 0.f;
   for (int i = lo; i <= hi; ++i) {
     // ---- per-lane: position, inside test, cell, density ----
     bool contributes = false;
@@ -385,15 +389,15 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_FWD_BLOCKS) render_fwd
     unsigned long long key = 0ull;  // 64-bit: voxel offset (up to 2^31) + the low corner's validity pattern
     const bool mine = marching && i >= s.i_lo && i <= s.i_hi;
     if (mine) {
-      if (!have_z) z = s.dg.at(i), have_z = true;
+      if (!have_z) dm.start(s.dg, i), z = dm.next(s.dg, i), have_z = true;
       last = (i == c.S - 1);
-      zn = last ? 0.0f : s.dg.at(i + 1);
+      zn = last ? 0.0f : dm.next(s.dg, i + 1);
       const float px = __fadd_rn(r.ox, __fmul_rn(r.dx, z));
       const float py = __fadd_rn(r.oy, __fmul_rn(r.dy, z));
       const float pz = __fadd_rn(r.oz, __fmul_rn(r.dz, z));
       if (inside_aabb(g, px, py, pz)) {
         Cell cell;
-        make_cell(g, px, py, pz, cell);
+        make_cell_inside(g, px, py, pz, cell);
         float dpost;
         sigma = density_post(g.post, density_pre_interp(g, cell), dpost);
         if (sigma != 0.0f) {
@@ -484,9 +488,238 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_FWD_BLOCKS) render_fwd
       }
       if (contributes) {
         const float delta = last ? __fmul_rn(kInfinity, s.dnorm) : __fmul_rn(__fsub_rn(zn, z), s.dnorm);
-        const float alpha = 1.0f - expf(-(sigma * delta));
+        const float alpha = 1.0f - exp_neg(sigma * delta);
         const float w = alpha * T;
         const float sr = sigmoidf_(rr), sg = sigmoidf_(rg), sb2 = sigmoidf_(rb);
+        if (out.cache) out.cache[(size_t)i * rp.n + ray] = make_float4(sr, sg, sb2, sigma);
+        cr = fmaf(w, sr, cr);
+        cg = fmaf(w, sg, cg);
+        cb = fmaf(w, sb2, cb);
+        dep = fmaf(w, z, dep);
+        acc += w;
+        T *= (1.0f - alpha);
+        if (T == 0.0f) marching = false;  // every later weight is alpha*0 = 0 exactly
+      }
+    }
+    if (mine) z = zn;
+  }
+  if (!alive) return;
+  if (c.flags & R3D_FLAG_WHITE_BKGD) {
+    const float bg = 1.0f - acc;
+    cr += bg, cg += bg, cb += bg;
+  }
+  out.colour[3 * ray] = cr, out.colour[3 * ray + 1] = cg, out.colour[3 * ray + 2] = cb;
+  out.depth[ray] = dep;
+  out.acc[ray] = acc;
+  if (out.disparity) {
+    const float ratio = __fdiv_rn(dep, acc);
+    const float m = (ratio != ratio) ? ratio : fmaxf(kZeroPlus, ratio);
+    out.disparity[ray] = __fdiv_rn(1.0f, m);
+  }
+}
+
+// =================================================================================================
+// forward, lane-group gather (default for the padded layouts, non-diffuse)
+//
+// Profile of render_fwd_coop_kernel (profiles/r01_v3_ncu_full_summary.md): 1.08 G shared-memory wavefronts per launch =
+// 75 % of all SM cycles.  Every contributing ray pulled its 8 x 112-byte records out of shared memory by itself
+// (56 LDS.128 per marching step, ~half the lanes idle because their sample has sigma == 0, and rays of the same cell
+// reading the same bytes again), on top of the staging writes.  Here a contributing sample is instead handed to a GROUP
+// of LPR consecutive lanes (8 at degree 2): lane `cj` of the group loads float4 `cj` of each of the 8 corner records
+// straight from global memory (one coalesced 112-byte read per record and group, 32/LPR samples per request), applies
+// the sample's 8 trilinear weights and its ray's SH basis to its 4 elements, and the group reduces the three channel
+// sums with 4 packed shuffles.  Nothing of the record passes through shared memory; what does is per SAMPLE, not per
+// record: 8 weights + 8 voxel offsets published by the owning lane, one float4 of the ray's (per-kernel constant)
+// expanded SH table per group lane, and the 3 results back.  All 32 lanes work on contributing samples only.
+// =================================================================================================
+template <int DEG>
+struct FwdGroupShape {
+  using S = CoopShape<DEG>;
+  static constexpr int LPR = S::LPR;        // lanes per sample (1, 4, 8, 16 for degree 0..3)
+  static constexpr int MPI = 32 / LPR;      // samples per iteration of a warp
+  static constexpr int YROW = 4 * S::NV;    // expanded SH row: Y[e % K] for record element e < F, 0 for the pad
+};
+
+template <int DEG>
+struct alignas(16) FwdGroupSmem {  // one per warp
+  using H = FwdGroupShape<DEG>;
+  float Y[32 * H::YROW];  // row per lane (= ray); written once per kernel
+  float W[32 * 8];        // rows per contributing sample of the current marching step (rank order)
+  unsigned V[32 * 8];     // corner record indices in float4 units
+  float R[32 * 4];        // raw radiance (r, g, b, -) per contributing sample
+  int src[32];            // owning lane of each rank
+};
+
+template <int DEG>
+__global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_FWD_BLOCKS) render_fwd_group_kernel(const GridP g, const RaysP rp, const CfgP c, const OutP out) {
+  using H = FwdGroupShape<DEG>;
+  using S = CoopShape<DEG>;
+  constexpr int K = S::K, F = S::F, NV = S::NV, LPR = H::LPR, MPI = H::MPI;
+  constexpr unsigned FULL = 0xffffffffu;
+  __shared__ __align__(16) FwdGroupSmem<DEG> smem_all[4];
+  FwdGroupSmem<DEG>& sm = smem_all[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
+
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long ray = thread_to_ray(rp, t);
+  const bool alive = ray >= 0;
+  RayCtx s;
+  s.i_lo = 1, s.i_hi = 0;
+  {
+    float Y[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) Y[k] = 0.f;
+    if (alive) {
+      float vx, vy, vz;
+      setup_ray(g, rp, c, ray, s, vx, vy, vz);
+      sh_basis<DEG>(vx, vy, vz, Y);
+    }
+    float* Yrow = sm.Y + lane * H::YROW;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      float q4[4];
+#pragma unroll
+      for (int l = 0; l < 4; ++l) q4[l] = (4 * j + l < F) ? Y[(4 * j + l) % K] : 0.0f;
+      *reinterpret_cast<float4*>(Yrow + 4 * j) = make_float4(q4[0], q4[1], q4[2], q4[3]);
+    }
+  }
+  const Ray& r = s.r;
+  bool marching = alive && s.i_lo <= s.i_hi;
+  int lo = marching ? s.i_lo : 0x7fffffff, hi = marching ? s.i_hi : -1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = min(lo, __shfl_xor_sync(FULL, lo, o));
+    hi = max(hi, __shfl_xor_sync(FULL, hi, o));
+  }
+  __syncwarp();  // SH table visible to the warp
+
+  // group role of this lane: float4 `cj` of the 8 corner records of sample `base + ms`
+  const int ms = lane / LPR, cj = lane % LPR;
+  const bool role_ok = cj < NV;
+  const unsigned stride4 = (unsigned)g.stride >> 2;  // record stride in float4s (the layout is a multiple of 4 floats)
+  const unsigned long long feat_lane = reinterpret_cast<unsigned long long>(g.feat) + 16ull * (unsigned)cj;
+  // Where this lane's channel sums end up after the group reduction (slot 0/1/2 = r/g/b of sm.R, -1 = nowhere), and, at
+  // degree 2 (K = 9: float4s 2 and 4 straddle a channel boundary), the lane it trades with in the second exchange.
+  int out_slot = -1, trade_lane = lane;
+  if constexpr (DEG == 1) out_slot = role_ok ? cj : -1;
+  if constexpr (DEG == 3) out_slot = (role_ok && (cj & 3) == 0) ? (cj >> 2) : -1;
+  if constexpr (DEG == 2) {
+    out_slot = cj == 0 ? 0 : (cj == 3 ? 1 : (cj == 5 ? 2 : -1));
+    const int x = (cj == 0 || cj == 2) ? 2 : ((cj == 3 || cj == 4) ? 7 : ((cj == 5 || cj == 6) ? 3 : 0));
+    trade_lane = lane ^ x;
+  }
+  const bool split1 = DEG == 2 && cj == 2, split2 = DEG == 2 && cj == 4, odd = (cj & 1) != 0;
+
+  float T = 1.0f, cr = 0.f, cg = 0.f, cb = 0.f, dep = 0.f, acc = 0.f;
+  float z = 0.f;
+  bool have_z = false;
+  DepthMarch dm;
+  dm.bm = dm.bc = 0.f;
+  for (int i = lo; i <= hi; ++i) {
+    // ---- per-lane: position, inside test, cell, density ----
+    bool contributes = false;
+    float sigma = 0.f, zn = 0.f;
+    bool last = false;
+    Cell cell;
+    const bool mine = marching && i >= s.i_lo && i <= s.i_hi;
+    if (mine) {
+      if (!have_z) dm.start(s.dg, i), z = dm.next(s.dg, i), have_z = true;
+      last = (i == c.S - 1);
+      zn = last ? 0.0f : dm.next(s.dg, i + 1);
+      const float px = __fadd_rn(r.ox, __fmul_rn(r.dx, z));
+      const float py = __fadd_rn(r.oy, __fmul_rn(r.dy, z));
+      const float pz = __fadd_rn(r.oz, __fmul_rn(r.dz, z));
+      if (inside_aabb(g, px, py, pz)) {
+        make_cell_inside(g, px, py, pz, cell);
+        float dpost;
+        sigma = density_post(g.post, density_pre_interp(g, cell), dpost);
+        contributes = sigma != 0.0f;
+      }
+    }
+    const unsigned act = __ballot_sync(FULL, contributes);
+    if (act != 0u) {
+      const int total = __popc(act);
+      const int rank = __popc(act & ((1u << lane) - 1u));
+      // ---- publish the sample: 8 corner weights, 8 corner record indices (in float4s; the launcher checked that
+      //      they fit 32 bits), owning lane ----
+      if (contributes) {
+        float wc[8];
+        unsigned rec4[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int ix = k >> 2, iy = (k >> 1) & 1, iz = k & 1;
+          wc[k] = cell.wx[ix] * cell.wy[iy] * cell.wz[iz];
+          rec4[k] = (unsigned)(cell.ox[ix] + cell.oy[iy] + cell.oz[iz]) * stride4;
+        }
+        float* Wrow = sm.W + rank * 8;
+        *reinterpret_cast<float4*>(Wrow) = make_float4(wc[0], wc[1], wc[2], wc[3]);
+        *reinterpret_cast<float4*>(Wrow + 4) = make_float4(wc[4], wc[5], wc[6], wc[7]);
+        unsigned* Vrow = sm.V + rank * 8;
+        *reinterpret_cast<uint4*>(Vrow) = make_uint4(rec4[0], rec4[1], rec4[2], rec4[3]);
+        *reinterpret_cast<uint4*>(Vrow + 4) = make_uint4(rec4[4], rec4[5], rec4[6], rec4[7]);
+        sm.src[rank] = lane;
+      }
+      __syncwarp();
+      // ---- lane groups: MPI samples per iteration ----
+      for (int base = 0; base < total; base += MPI) {
+        const int m = base + ms;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m < total && role_ok) {
+          const float4 w0 = *reinterpret_cast<const float4*>(sm.W + m * 8);
+          const float4 w1 = *reinterpret_cast<const float4*>(sm.W + m * 8 + 4);
+          const uint4 v0 = *reinterpret_cast<const uint4*>(sm.V + m * 8);
+          const uint4 v1 = *reinterpret_cast<const uint4*>(sm.V + m * 8 + 4);
+          const float4 y4 = *reinterpret_cast<const float4*>(sm.Y + sm.src[m] * H::YROW + 4 * cj);
+          const float wk[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+          const unsigned vk[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+          float4 q[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {  // all 8 loads in flight; address = lane base + 16 * record index
+            unsigned long long addr;
+            asm("mad.wide.u32 %0, %1, 16, %2;" : "=l"(addr) : "r"(vk[k]), "l"(feat_lane));
+            q[k] = __ldg(reinterpret_cast<const float4*>(addr));
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            a.x = fmaf(wk[k], q[k].x, a.x), a.y = fmaf(wk[k], q[k].y, a.y);
+            a.z = fmaf(wk[k], q[k].z, a.z), a.w = fmaf(wk[k], q[k].w, a.w);
+          }
+          a.x *= y4.x, a.y *= y4.y, a.z *= y4.z, a.w *= y4.w;  // the pad element has Y = 0
+        }
+        // ---- channel sums of the group.  The record is channel-major (coeff[ch][k] = rec[ch * K + k]). ----
+        if constexpr (DEG == 0) {  // one lane per sample, elements 0..2 are the three channels
+          if (m < total) *reinterpret_cast<float4*>(sm.R + m * 4) = a;
+        } else {
+          const float u01 = a.x + a.y, u23 = a.z + a.w;
+          float v;
+          if constexpr (DEG == 2) {
+            // float4 2 = {r8 | g0 g1 g2}, float4 4 = {g7 g8 | b0 b1}; every other float4 lies inside one channel.
+            // A = part of the lane's first channel, B = part of its second one (0 for unsplit lanes).
+            const float A = split1 ? a.x : (split2 ? u01 : u01 + u23);
+            const float B = split1 ? a.y + u23 : (split2 ? u23 : 0.0f);
+            // exchange 1 (xor 1): even lanes take the neighbour's A, odd lanes the neighbour's B:
+            //   lane 0: r(0,1)   lane 3: g = B2 + A3   lane 5: b = B4 + A5;  lanes 2, 4, 6 keep their own A
+            const float x = __shfl_xor_sync(FULL, odd ? A : B, 1);
+            v = (split1 || split2) ? A : A + x;
+            // exchange 2: r = lane 0 + lane 2, g = lane 3 + lane 4, b = lane 5 + lane 6
+            v += __shfl_sync(FULL, v, trade_lane);
+          } else {
+            v = u01 + u23;
+            if constexpr (DEG == 3) {  // 4 lanes per channel
+              v += __shfl_xor_sync(FULL, v, 1);
+              v += __shfl_xor_sync(FULL, v, 2);
+            }
+          }
+          if (m < total && out_slot >= 0) sm.R[m * 4 + out_slot] = v;
+        }
+      }
+      __syncwarp();
+      if (contributes) {
+        const float4 raw = *reinterpret_cast<const float4*>(sm.R + rank * 4);
+        const float delta = last ? __fmul_rn(kInfinity, s.dnorm) : __fmul_rn(__fsub_rn(zn, z), s.dnorm);
+        const float alpha = 1.0f - exp_neg(sigma * delta);
+        const float w = alpha * T;
+        const float sr = sigmoidf_(raw.x), sg = sigmoidf_(raw.y), sb2 = sigmoidf_(raw.z);
         if (out.cache) out.cache[(size_t)i * rp.n + ray] = make_float4(sr, sg, sb2, sigma);
         cr = fmaf(w, sr, cr);
         cg = fmaf(w, sg, cg);
@@ -580,21 +813,23 @@ __global__ void __launch_bounds__(128) render_bwd_kernel(const GridP g, const Ra
   if (s.i_lo > s.i_hi) return;
   // |q_i| <= |g_c|_1 + |g_d| z_max + |g_a|  (z is monotone and non-negative along the marched range)
   const float qmax = fabsf(gc[0]) + fabsf(gc[1]) + fabsf(gc[2]) + fabsf(gd) * fmaxf(fabsf(s.dg.near), fabsf(s.dg.far)) + fabsf(ga);
-  float z = s.dg.at(s.i_lo);
+  DepthMarch dm;
+  dm.start(s.dg, s.i_lo);
+  float z = dm.next(s.dg, s.i_lo);
   for (int i = s.i_lo; i <= s.i_hi; ++i) {
     const bool last = (i == c.S - 1);
-    const float zn = last ? 0.0f : s.dg.at(i + 1);
+    const float zn = last ? 0.0f : dm.next(s.dg, i + 1);
     const float px = __fadd_rn(r.ox, __fmul_rn(r.dx, z));
     const float py = __fadd_rn(r.oy, __fmul_rn(r.dy, z));
     const float pz = __fadd_rn(r.oz, __fmul_rn(r.dz, z));
     if (inside_aabb(g, px, py, pz)) {
       Cell cell;
-      make_cell(g, px, py, pz, cell);
+      make_cell_inside(g, px, py, pz, cell);
       float dpost;
       const float sigma = density_post(g.post, density_pre_interp(g, cell), dpost);
       if (sigma != 0.0f || dpost != 0.0f) {
         const float delta = last ? __fmul_rn(kInfinity, s.dnorm) : __fmul_rn(__fsub_rn(zn, z), s.dnorm);
-        const float alpha = 1.0f - expf(-(sigma * delta));
+        const float alpha = 1.0f - exp_neg(sigma * delta);
         const float w = alpha * T;
         const float Tn = T * (1.0f - alpha);
         float sr, sg, sb;
@@ -725,6 +960,8 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_BWD_BLOCKS) render_bwd
   float T = 1.0f, prefix = 0.f;
   float z = 0.f;
   bool have_z = false;
+  DepthMarch dm;
+  dm.bm = dm.bc = 0.f;
   for (int i = lo; i <= hi; ++i) {
     // ------------------------------------------------------------------ 1. per-lane sample maths
     bool contributes = false;
@@ -733,20 +970,20 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_BWD_BLOCKS) render_bwd
     float draw[3] = {0.f, 0.f, 0.f}, dpre = 0.f;
     unsigned long long key = 0ull;  // 64-bit: voxel offset (up to 2^31) + the low corner's validity pattern
     if (alive && i >= s.i_lo && i <= s.i_hi) {
-      if (!have_z) z = s.dg.at(i), have_z = true;
+      if (!have_z) dm.start(s.dg, i), z = dm.next(s.dg, i), have_z = true;
       const bool last = (i == c.S - 1);
-      const float zn = last ? 0.0f : s.dg.at(i + 1);
+      const float zn = last ? 0.0f : dm.next(s.dg, i + 1);
       const float px = __fadd_rn(r.ox, __fmul_rn(r.dx, z));
       const float py = __fadd_rn(r.oy, __fmul_rn(r.dy, z));
       const float pz = __fadd_rn(r.oz, __fmul_rn(r.dz, z));
       if (inside_aabb(g, px, py, pz)) {
         Cell cell;
-        make_cell(g, px, py, pz, cell);
+        make_cell_inside(g, px, py, pz, cell);
         float dpost;
         const float sigma = density_post(g.post, density_pre_interp(g, cell), dpost);
         if (sigma != 0.0f || dpost != 0.0f) {
           const float delta = last ? __fmul_rn(kInfinity, s.dnorm) : __fmul_rn(__fsub_rn(zn, z), s.dnorm);
-          const float alpha = 1.0f - expf(-(sigma * delta));
+          const float alpha = 1.0f - exp_neg(sigma * delta);
           const float w = alpha * T;
           const float Tn = T * (1.0f - alpha);
           float sr, sg, sb;
@@ -894,7 +1131,7 @@ __global__ void __launch_bounds__(128) mark_touched_kernel(const GridP g, const 
     const float pz = __fadd_rn(r.oz, __fmul_rn(r.dz, z));
     if (!inside_aabb(g, px, py, pz)) continue;
     Cell cell;
-    make_cell(g, px, py, pz, cell);
+    make_cell_inside(g, px, py, pz, cell);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int ix = k >> 2, iy = (k >> 1) & 1, iz = k & 1;
@@ -914,8 +1151,12 @@ static void launch_fwd(int vec, int variant, dim3 grid, cudaStream_t st, const G
   if (vec != 0 && !diffuse && !(variant & 2)) {
     if (variant & 4)  // TMA (cp.async.bulk) staging instead of per-lane cp.async: measured, see DESIGN.md
       render_fwd_coop_kernel<DEG, true><<<grid, 128, 0, st>>>(g, r, c, o);
-    else
+    else if ((variant & 8) || (unsigned long long)g.W * g.D * g.H * (unsigned long long)(g.stride / 4) > 0xffffffffull)
+      // shared-memory staged gather (the default before the lane-group kernel, which addresses records with 32-bit
+      // float4 indices; no supported grid exceeds them: 512^3 at degree 3 is 1.6 G)
       render_fwd_coop_kernel<DEG, false><<<grid, 128, 0, st>>>(g, r, c, o);
+    else
+      render_fwd_group_kernel<DEG><<<grid, 128, 0, st>>>(g, r, c, o);
     return;
   }
   if (vec == 8)
