@@ -434,7 +434,7 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "render_bwd_coop_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes": bytes_bwd, "kernel_ms": bwd_ms},
-            "roofline_fwd": {"bound": "hbm", "kernel": "render_fwd_coop_kernel", "achieved": bytes_fwd / (fwd_ms * 1e-3) / 1e9,
+            "roofline_fwd": {"bound": "hbm", "kernel": "render_fwd_group_kernel", "achieved": bytes_fwd / (fwd_ms * 1e-3) / 1e9,
                              "peak": peak, "unit": "GB/s", "frac": bytes_fwd / (fwd_ms * 1e-3) / 1e9 / peak,
                              "algorithmic_bytes": bytes_fwd, "kernel_ms": fwd_ms},
             "unique_voxels_touched": touched, "voxel_record_bytes": rec_bytes,

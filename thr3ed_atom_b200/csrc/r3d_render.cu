@@ -32,11 +32,17 @@
 // cover consecutive bytes of ONE voxel record and merge samples that share an interpolation cell.
 #include "r3d_host.h"
 
+#include <cstdlib>
+
 // resident CTAs per SM the cooperative kernels are compiled for (register budget = 65536 / (128 * blocks)).
 // Measured at c3 on the B200: backward 7.95 ms at 4 CTAs/SM, 7.45 ms at 5 (96 registers, a few bytes of spill);
 // forward unchanged between 4 and 5.
 #ifndef R3D_FWD_BLOCKS
 #define R3D_FWD_BLOCKS 4
+#endif
+// forward lane-group kernel: software-pipelined record loads (two register buffers)
+#ifndef R3D_FWD_PIPE
+#define R3D_FWD_PIPE 0  // measured at c3: 5.44 ms pipelined vs 4.41 ms (4 CTAs/SM), 5.40 vs 5.29 ms (3 CTAs/SM)
 #endif
 #ifndef R3D_BWD_BLOCKS
 #define R3D_BWD_BLOCKS 5
@@ -660,25 +666,29 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_FWD_BLOCKS) render_fwd
         sm.src[rank] = lane;
       }
       __syncwarp();
-      // ---- lane groups: MPI samples per iteration ----
-      for (int base = 0; base < total; base += MPI) {
-        const int m = base + ms;
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      // ---- lane groups: MPI samples per iteration.  issue() puts the 8 record loads of a sample in flight, finish()
+      //      applies weights and SH basis and reduces over the group; the loads of iteration n + 1 are issued before
+      //      iteration n is finished (two register buffers), so only the first load latency of a step is exposed.
+      auto issue = [&](int m, float4(&q)[8]) {
         if (m < total && role_ok) {
-          const float4 w0 = *reinterpret_cast<const float4*>(sm.W + m * 8);
-          const float4 w1 = *reinterpret_cast<const float4*>(sm.W + m * 8 + 4);
           const uint4 v0 = *reinterpret_cast<const uint4*>(sm.V + m * 8);
           const uint4 v1 = *reinterpret_cast<const uint4*>(sm.V + m * 8 + 4);
-          const float4 y4 = *reinterpret_cast<const float4*>(sm.Y + sm.src[m] * H::YROW + 4 * cj);
-          const float wk[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
           const unsigned vk[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-          float4 q[8];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {  // all 8 loads in flight; address = lane base + 16 * record index
+          for (int k = 0; k < 8; ++k) {  // address = lane base + 16 * record index
             unsigned long long addr;
             asm("mad.wide.u32 %0, %1, 16, %2;" : "=l"(addr) : "r"(vk[k]), "l"(feat_lane));
             q[k] = __ldg(reinterpret_cast<const float4*>(addr));
           }
+        }
+      };
+      auto finish = [&](int m, const float4(&q)[8]) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m < total && role_ok) {
+          const float4 w0 = *reinterpret_cast<const float4*>(sm.W + m * 8);
+          const float4 w1 = *reinterpret_cast<const float4*>(sm.W + m * 8 + 4);
+          const float4 y4 = *reinterpret_cast<const float4*>(sm.Y + sm.src[m] * H::YROW + 4 * cj);
+          const float wk[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             a.x = fmaf(wk[k], q[k].x, a.x), a.y = fmaf(wk[k], q[k].y, a.y);
@@ -712,7 +722,30 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_FWD_BLOCKS) render_fwd
           }
           if (m < total && out_slot >= 0) sm.R[m * 4 + out_slot] = v;
         }
+      };
+#if R3D_FWD_PIPE
+      {
+        float4 qa[8], qb[8];
+        int base = 0;
+        issue(ms, qa);
+        while (true) {  // `base`, `total` are warp-uniform: every lane takes the same path
+          if (base + MPI < total) issue(base + MPI + ms, qb);
+          finish(base + ms, qa);
+          base += MPI;
+          if (base >= total) break;
+          if (base + MPI < total) issue(base + MPI + ms, qa);
+          finish(base + ms, qb);
+          base += MPI;
+          if (base >= total) break;
+        }
       }
+#else
+      for (int base = 0; base < total; base += MPI) {
+        float4 q[8];
+        issue(base + ms, q);
+        finish(base + ms, q);
+      }
+#endif
       __syncwarp();
       if (contributes) {
         const float4 raw = *reinterpret_cast<const float4*>(sm.R + rank * 4);
@@ -1155,8 +1188,17 @@ static void launch_fwd(int vec, int variant, dim3 grid, cudaStream_t st, const G
       // shared-memory staged gather (the default before the lane-group kernel, which addresses records with 32-bit
       // float4 indices; no supported grid exceeds them: 512^3 at degree 3 is 1.6 G)
       render_fwd_coop_kernel<DEG, false><<<grid, 128, 0, st>>>(g, r, c, o);
-    else
+    else {
+      // tuning hook: $R3D_FWD_CARVEOUT = preferred shared-memory carve-out in percent (the rest of the 228 KB is L1)
+      static const int carve = [] {
+        const char* e = getenv("R3D_FWD_CARVEOUT");
+        const int v = e ? atoi(e) : -1;
+        if (v >= 0) cudaFuncSetAttribute(render_fwd_group_kernel<DEG>, cudaFuncAttributePreferredSharedMemoryCarveout, v);
+        return v;
+      }();
+      (void)carve;
       render_fwd_group_kernel<DEG><<<grid, 128, 0, st>>>(g, r, c, o);
+    }
     return;
   }
   if (vec == 8)
