@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define R3D_ABI_VERSION 2
+#define R3D_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define R3D_API __attribute__((visibility("default")))
@@ -116,6 +116,13 @@ typedef struct R3dRenderOut {
                           sample with sigma != 0 is stored at [sample][ray] (other entries are left untouched).  Backward
                           (`saved`): when non-NULL the per-sample radiance is read back instead of being re-gathered from
                           the grid.  Trades 16*N*S bytes of HBM for the second 8-corner gather. */
+  /* Single-pass specular + diffuse render.  The reference trainer renders every batch twice, once with
+   * all SH bands and once with band 0 only (modules/trainers.py:306-330, process.py:59-63); the diffuse radiance is the
+   * k = 0 slice of the very records the specular render interpolates, so one gather serves both.  When `colour_diffuse`
+   * is non-NULL (R3D_FLAG_DIFFUSE must be clear) the forward also writes the band-0 image of the SAME samples there;
+   * depth, acc and disparity are common to both (they do not depend on the radiance). */
+  float* colour_diffuse;        /* [N][3], optional */
+  float* sample_cache_diffuse;  /* optional [S][N][4] like sample_cache: (sigmoid(raw_diffuse) rgb, -) per sample */
 } R3dRenderOut;
 
 /* upstream gradients dL/d(output); any pointer may be NULL (= zero). */
@@ -124,6 +131,7 @@ typedef struct R3dRenderOutGrad {
   const float* depth;      /* [N] */
   const float* acc;        /* [N] */
   const float* disparity;  /* [N] */
+  const float* colour_diffuse;  /* [N][3]: dL/d(colour_diffuse) of a single-pass specular + diffuse render */
 } R3dRenderOutGrad;
 
 /* gradient buffers, same layout as R3dGrid.densities / .features; accumulated into. */

@@ -7,20 +7,21 @@ rep, which = sys.argv[1], sys.argv[2]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 MARK = {
-    "fwd": [("render_fwd_group_kernel(const GridP", "setup"), ("// ---- per-lane: position, inside test, cell, density", "march+density"),
-            ("const unsigned act = __ballot_sync", "publish"), ("// ---- lane groups", "group loop"),
+    "fwd": [("render_fwd_group_kernel(const GridP", "setup"), ("const bool mine = marching", "march+density"),
+            ("const unsigned act = __ballot_sync", "publish"), ("if (m < total && role_ok) {", "group loop"),
             ("const float4 raw = ", "composite"), ("if (!alive) return;", "epilogue"), ("struct RayGrad", "other")],
-    "bwd": [("render_bwd_coop_kernel(const GridP", "setup"), ("// ------------------------------------------------------------------ 1. per-lane", "march+density+chain"),
-            ("// ------------------------------------------------------------------ 2. publish", "publish"),
-            ("// ------------------------------------------------------------------ 3. group", "match+leaders"),
-            ("while (mm) {", "member sweep"), ("const int* VL = ", "scatter"), ("// measurement helper", "other")],
+    "bwd": [("render_bwd_coop_kernel(const GridP", "setup"), ("if (alive && i >= s.i_lo", "per-lane chain maths"),
+            ("float* Prow = sm.P", "publish"), ("peers = __match_any_sync", "match+leaders"),
+            ("while (mm) {", "member sweep"), ("const int* VL = ", "scatter"), ("mark_touched_kernel", "other")],
 }[which]
-cur = None; hdr = None; lines = []
+cur = None; hdr = None; lines = []; func = ""
+want = "render_fwd" if which == "fwd" else "render_bwd"
 for r in rows:
     if not r: continue
     if r[0] == "File Path": cur = r[1].split("/")[-1]; continue
     if r[0] == "Line No": hdr = r; continue
-    if r[0] == "Function Name": continue
+    if r[0] == "Function Name": func = r[1]; continue
+    if want not in func: continue
     if r[0] != "" and hdr:
         try: ln = int(r[0])
         except ValueError: continue

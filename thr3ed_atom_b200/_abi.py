@@ -13,7 +13,7 @@ from typing import Optional
 
 # $R3D_LIB_PATH selects another build of the same library (tuning experiments: other -D flags); default = the in-tree build
 LIB_PATH = Path(os.environ.get("R3D_LIB_PATH") or (Path(__file__).resolve().parent / "_lib" / "libr3d_b200.so"))
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # enums of r3d_b200.h
 PRE_IDENTITY, PRE_ABS = 0, 1
@@ -76,11 +76,12 @@ class R3dRenderConfig(C.Structure):
 
 
 class R3dRenderOut(C.Structure):
-    _fields_ = [("colour", C.c_void_p), ("depth", C.c_void_p), ("acc", C.c_void_p), ("disparity", C.c_void_p), ("sample_cache", C.c_void_p)]
+    _fields_ = [("colour", C.c_void_p), ("depth", C.c_void_p), ("acc", C.c_void_p), ("disparity", C.c_void_p), ("sample_cache", C.c_void_p),
+                ("colour_diffuse", C.c_void_p), ("sample_cache_diffuse", C.c_void_p)]
 
 
 class R3dRenderOutGrad(C.Structure):
-    _fields_ = [("colour", C.c_void_p), ("depth", C.c_void_p), ("acc", C.c_void_p), ("disparity", C.c_void_p)]
+    _fields_ = [("colour", C.c_void_p), ("depth", C.c_void_p), ("acc", C.c_void_p), ("disparity", C.c_void_p), ("colour_diffuse", C.c_void_p)]
 
 
 class R3dGridGrad(C.Structure):

@@ -152,11 +152,14 @@ def new_sample_cache(num_rays: int, num_samples: int, device) -> Tensor:
 
 
 def render_forward(grid: GridDesc, origins: Optional[Tensor], directions: Optional[Tensor], args: RenderArgs,
-                   sample_cache: Optional[Tensor] = None):
+                   sample_cache: Optional[Tensor] = None, with_diffuse: bool = False, sample_cache_diffuse: Optional[Tensor] = None):
     """Fused forward render.  Returns ``(colour [N,3], depth [N,1], acc [N,1], disparity [N,1])``.
-    ``sample_cache`` (``new_sample_cache``) is filled for the backward pass when given."""
+    ``sample_cache`` (``new_sample_cache``) is filled for the backward pass when given.
+    ``with_diffuse``: single-pass specular + diffuse render -- a fifth return value ``colour_diffuse [N,3]`` is the band-0
+    image of the same samples (``sample_cache_diffuse``: its per-sample records for the backward)."""
     device = grid.features.device
     n = origins.shape[0] if args.camera is None else int(args.camera[0]) * int(args.camera[1])
+    colour_diffuse = torch.empty((n, 3), dtype=torch.float32, device=device) if with_diffuse else None
     colour = torch.empty((n, 3), dtype=torch.float32, device=device)
     depth = torch.empty((n, 1), dtype=torch.float32, device=device)
     acc = torch.empty((n, 1), dtype=torch.float32, device=device)
@@ -166,10 +169,17 @@ def render_forward(grid: GridDesc, origins: Optional[Tensor], directions: Option
         _require_cuda(sample_cache, "sample_cache")
         if tuple(sample_cache.shape) != (args.num_samples, n, 4) or not sample_cache.is_contiguous():
             raise ValueError(f"sample_cache must be a contiguous [{args.num_samples}, {n}, 4] tensor")
-    out = _abi.R3dRenderOut(colour.data_ptr(), depth.data_ptr(), acc.data_ptr(), disparity.data_ptr(), _ptr(sample_cache))
+    if sample_cache_diffuse is not None:
+        _require_cuda(sample_cache_diffuse, "sample_cache_diffuse")
+        if not with_diffuse or tuple(sample_cache_diffuse.shape) != (args.num_samples, n, 4) or not sample_cache_diffuse.is_contiguous():
+            raise ValueError(f"sample_cache_diffuse needs with_diffuse and a contiguous [{args.num_samples}, {n}, 4] tensor")
+    out = _abi.R3dRenderOut(colour.data_ptr(), depth.data_ptr(), acc.data_ptr(), disparity.data_ptr(), _ptr(sample_cache),
+                            _ptr(colour_diffuse), _ptr(sample_cache_diffuse))
     with torch.cuda.device(device):
         _abi.check(_abi.lib().r3d_render_fwd(C.byref(g), C.byref(r), C.byref(c), C.byref(out), _stream(device)), "r3d_render_fwd")
     del keep
+    if with_diffuse:
+        return colour, depth, acc, disparity, colour_diffuse
     return colour, depth, acc, disparity
 
 
@@ -183,16 +193,21 @@ def render_backward(
     grad_densities: Optional[Tensor],
     grad_features: Optional[Tensor],
     sample_cache: Optional[Tensor] = None,
+    diffuse: Optional[Tuple[Tensor, Optional[Tensor], Optional[Tensor]]] = None,
 ) -> None:
     """Fused backward: accumulates into ``grad_densities`` / ``grad_features`` (same layout as the grid).
-    ``sample_cache`` must be the buffer the matching forward call filled (else the radiance is re-gathered)."""
+    ``sample_cache`` must be the buffer the matching forward call filled (else the radiance is re-gathered).
+    ``diffuse`` = ``(colour_diffuse, grad_colour_diffuse, sample_cache_diffuse)`` of a single-pass specular + diffuse render."""
     device = grid.features.device
     colour, depth, acc = saved
     n = colour.shape[0]
     g, r, c, keep = _pack_call(grid, origins, directions, n, args)
-    sv = _abi.R3dRenderOut(colour.data_ptr(), depth.data_ptr(), acc.data_ptr(), None, _ptr(sample_cache))
+    colour_d, grad_colour_d, cache_d = diffuse if diffuse is not None else (None, None, None)
+    if grad_colour_d is not None:
+        grad_colour_d = _require_cuda(grad_colour_d.contiguous(), "grad_output")
+    sv = _abi.R3dRenderOut(colour.data_ptr(), depth.data_ptr(), acc.data_ptr(), None, _ptr(sample_cache), _ptr(colour_d), _ptr(cache_d))
     gs = [None if t is None else _require_cuda(t.contiguous(), "grad_output") for t in grads]
-    go = _abi.R3dRenderOutGrad(*[_ptr(t) for t in gs])
+    go = _abi.R3dRenderOutGrad(*[_ptr(t) for t in gs], _ptr(grad_colour_d))
     for t, ref in ((grad_densities, grid.densities), (grad_features, grid.features)):
         if t is not None and (tuple(t.shape) != tuple(ref.shape) or not t.is_contiguous() or t.dtype != torch.float32):
             raise ValueError("gradient buffers must match the grid storage layout")

@@ -56,6 +56,8 @@ struct OutP {
   float* __restrict__ acc;
   float* __restrict__ disparity;
   float4* __restrict__ cache;  // optional [S][N] (sigmoid(raw) rgb, sigma) of every sigma != 0 sample, for the backward
+  float* __restrict__ colour_diffuse;  // single-pass specular + diffuse render: band-0 image of the same samples
+  float4* __restrict__ cache_diffuse;  // optional [S][N] (sigmoid(raw_diffuse) rgb, -)
 };
 
 struct BwdP {
@@ -69,6 +71,9 @@ struct BwdP {
   float* __restrict__ gdens;  // outputs (nullable)
   float* __restrict__ gfeat;
   const float4* __restrict__ cache;  // optional sample cache written by the forward pass
+  const float* __restrict__ colour_diffuse;    // single-pass specular + diffuse render: saved band-0 image,
+  const float* __restrict__ g_colour_diffuse;  //   its upstream gradient (nullable)
+  const float4* __restrict__ cache_diffuse;    //   and its per-sample records
 };
 
 struct RayCtx {
@@ -546,24 +551,29 @@ struct FwdGroupShape {
   static constexpr int YROW = 4 * S::NV;    // expanded SH row: Y[e % K] for record element e < F, 0 for the pad
 };
 
-template <int DEG>
+template <int DEG, bool DUAL>
 struct alignas(16) FwdGroupSmem {  // one per warp
   using H = FwdGroupShape<DEG>;
   float Y[32 * H::YROW];  // row per lane (= ray); written once per kernel
   float W[32 * 8];        // rows per contributing sample of the current marching step (rank order)
   unsigned V[32 * 8];     // corner record indices in float4 units
   float R[32 * 4];        // raw radiance (r, g, b, -) per contributing sample
+  float R2[DUAL ? 32 * 4 : 4];  // raw band-0 ("diffuse") radiance of the same samples (single-pass specular + diffuse render)
   int src[32];            // owning lane of each rank
 };
 
-template <int DEG>
+// DUAL: also produce the band-0 ("diffuse", process.py:59-63) image of the same samples (reference trainer:
+// modules/trainers.py:306-330 renders every batch twice).  raw_diffuse[ch] = C0 * coeff[ch][0] is the k = 0 element of
+// the record the specular render interpolates anyway: the lanes that hold elements 0, K, 2K hand it over before the SH
+// weighting, everything else (samples, density, weights, depth, acc) is shared.
+template <int DEG, bool DUAL>
 __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_FWD_BLOCKS) render_fwd_group_kernel(const GridP g, const RaysP rp, const CfgP c, const OutP out) {
   using H = FwdGroupShape<DEG>;
   using S = CoopShape<DEG>;
   constexpr int K = S::K, F = S::F, NV = S::NV, LPR = H::LPR, MPI = H::MPI;
   constexpr unsigned FULL = 0xffffffffu;
-  __shared__ __align__(16) FwdGroupSmem<DEG> smem_all[4];
-  FwdGroupSmem<DEG>& sm = smem_all[threadIdx.x >> 5];
+  __shared__ __align__(16) FwdGroupSmem<DEG, DUAL> smem_all[4];
+  FwdGroupSmem<DEG, DUAL>& sm = smem_all[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
 
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -615,6 +625,12 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_FWD_BLOCKS) render_fwd
     trade_lane = lane ^ x;
   }
   const bool split1 = DEG == 2 && cj == 2, split2 = DEG == 2 && cj == 4, odd = (cj & 1) != 0;
+  // DUAL: element ch * K (coefficient k = 0 of channel ch) sits in float4 (ch * K) / 4, component (ch * K) % 4
+  int dslot = -1, dcomp = 0;
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch)
+    if (DUAL && DEG > 0 && cj == (ch * K) / 4) dslot = ch, dcomp = (ch * K) % 4;
+  float cdr = 0.f, cdg = 0.f, cdb = 0.f;
 
   float T = 1.0f, cr = 0.f, cg = 0.f, cb = 0.f, dep = 0.f, acc = 0.f;
   float z = 0.f;
@@ -694,6 +710,9 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_FWD_BLOCKS) render_fwd
             a.x = fmaf(wk[k], q[k].x, a.x), a.y = fmaf(wk[k], q[k].y, a.y);
             a.z = fmaf(wk[k], q[k].z, a.z), a.w = fmaf(wk[k], q[k].w, a.w);
           }
+          if constexpr (DUAL && DEG > 0) {  // band-0 radiance: C0 * interpolated coeff[ch][0] (Y[0] = C0 for every ray)
+            if (dslot >= 0) sm.R2[m * 4 + dslot] = 0.28209479177387814f * (dcomp == 0 ? a.x : (dcomp == 1 ? a.y : (dcomp == 2 ? a.z : a.w)));
+          }
           a.x *= y4.x, a.y *= y4.y, a.z *= y4.z, a.w *= y4.w;  // the pad element has Y = 0
         }
         // ---- channel sums of the group.  The record is channel-major (coeff[ch][k] = rec[ch * K + k]). ----
@@ -757,6 +776,15 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_FWD_BLOCKS) render_fwd
         cr = fmaf(w, sr, cr);
         cg = fmaf(w, sg, cg);
         cb = fmaf(w, sb2, cb);
+        if constexpr (DUAL) {
+          // degree 0 has no higher bands: the diffuse radiance is the specular one
+          const float4 raw2 = DEG > 0 ? *reinterpret_cast<const float4*>(sm.R2 + rank * 4) : raw;
+          const float dr = sigmoidf_(raw2.x), dg_ = sigmoidf_(raw2.y), db = sigmoidf_(raw2.z);
+          if (out.cache_diffuse) out.cache_diffuse[(size_t)i * rp.n + ray] = make_float4(dr, dg_, db, 0.0f);
+          cdr = fmaf(w, dr, cdr);
+          cdg = fmaf(w, dg_, cdg);
+          cdb = fmaf(w, db, cdb);
+        }
         dep = fmaf(w, z, dep);
         acc += w;
         T *= (1.0f - alpha);
@@ -769,8 +797,10 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_FWD_BLOCKS) render_fwd
   if (c.flags & R3D_FLAG_WHITE_BKGD) {
     const float bg = 1.0f - acc;
     cr += bg, cg += bg, cb += bg;
+    cdr += bg, cdg += bg, cdb += bg;
   }
   out.colour[3 * ray] = cr, out.colour[3 * ray + 1] = cg, out.colour[3 * ray + 2] = cb;
+  if constexpr (DUAL) out.colour_diffuse[3 * ray] = cdr, out.colour_diffuse[3 * ray + 1] = cdg, out.colour_diffuse[3 * ray + 2] = cdb;
   out.depth[ray] = dep;
   out.acc[ray] = acc;
   if (out.disparity) {
@@ -784,10 +814,14 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_FWD_BLOCKS) render_fwd
 // Total = sum_i w_i q_i rebuilt from the forward outputs.  Returns false when the ray receives no gradient.
 struct RayGrad {
   float gc[3], gd, ga, total;
+  float gcd[3];  // upstream gradient of the band-0 ("diffuse") image of a single-pass specular + diffuse render
 };
 __device__ __forceinline__ bool load_ray_grad(const BwdP& b, const CfgP& c, long long ray, RayGrad& rg) {
   float* gc = rg.gc;
   gc[0] = gc[1] = gc[2] = 0.f;
+  float* gcd = rg.gcd;
+  gcd[0] = gcd[1] = gcd[2] = 0.f;
+  if (b.g_colour_diffuse) gcd[0] = __ldg(b.g_colour_diffuse + 3 * ray), gcd[1] = __ldg(b.g_colour_diffuse + 3 * ray + 1), gcd[2] = __ldg(b.g_colour_diffuse + 3 * ray + 2);
   float gd = 0.f, ga = 0.f;
   if (b.g_colour) gc[0] = __ldg(b.g_colour + 3 * ray), gc[1] = __ldg(b.g_colour + 3 * ray + 1), gc[2] = __ldg(b.g_colour + 3 * ray + 2);
   if (b.g_depth) gd = __ldg(b.g_depth + ray);
@@ -808,14 +842,21 @@ __device__ __forceinline__ bool load_ray_grad(const BwdP& b, const CfgP& c, long
     }
   }
   float cfr = __ldg(b.colour + 3 * ray), cfg_ = __ldg(b.colour + 3 * ray + 1), cfb = __ldg(b.colour + 3 * ray + 2);
+  float dfr = 0.f, dfg = 0.f, dfb = 0.f;
+  if (b.g_colour_diffuse) dfr = __ldg(b.colour_diffuse + 3 * ray), dfg = __ldg(b.colour_diffuse + 3 * ray + 1), dfb = __ldg(b.colour_diffuse + 3 * ray + 2);
   if (c.flags & R3D_FLAG_WHITE_BKGD) {
     const float bg = 1.0f - acc_f;
     cfr -= bg, cfg_ -= bg, cfb -= bg;
     ga -= (gc[0] + gc[1] + gc[2]);  // d(1 - acc)/d acc on every channel
+    if (b.g_colour_diffuse) {
+      dfr -= bg, dfg -= bg, dfb -= bg;
+      ga -= (gcd[0] + gcd[1] + gcd[2]);
+    }
   }
   rg.gd = gd, rg.ga = ga;
   rg.total = fmaf(gc[0], cfr, fmaf(gc[1], cfg_, fmaf(gc[2], cfb, fmaf(gd, dep_f, ga * acc_f))));
-  return !(gc[0] == 0.f && gc[1] == 0.f && gc[2] == 0.f && gd == 0.f && ga == 0.f);
+  rg.total = fmaf(gcd[0], dfr, fmaf(gcd[1], dfg, fmaf(gcd[2], dfb, rg.total)));
+  return !(gc[0] == 0.f && gc[1] == 0.f && gc[2] == 0.f && gd == 0.f && ga == 0.f && gcd[0] == 0.f && gcd[1] == 0.f && gcd[2] == 0.f);
 }
 
 // =================================================================================================
@@ -945,7 +986,9 @@ struct alignas(16) CoopSmem {
   float D[32];
 };
 
-template <int DEG, int VEC>
+// DUAL: backward of the single-pass specular + diffuse render: the band-0 image adds g_cd . sigmoid(raw_d_i) to q_i and
+// d raw_d[ch] * Y[0] to element ch * K of the product row; nothing else changes (same samples, same weights).
+template <int DEG, int VEC, bool DUAL>
 __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_BWD_BLOCKS) render_bwd_coop_kernel(const GridP g, const RaysP rp, const CfgP c, const BwdP b) {
   using S = CoopShape<DEG>;
   constexpr int K = S::K, F = S::F;
@@ -969,6 +1012,7 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_BWD_BLOCKS) render_bwd
     setup_ray(g, rp, c, ray, s, vx, vy, vz);
     sh_basis<DEG>(vx, vy, vz, Y);
     qmax = fabsf(rgd.gc[0]) + fabsf(rgd.gc[1]) + fabsf(rgd.gc[2]) + fabsf(rgd.gd) * fmaxf(fabsf(s.dg.near), fabsf(s.dg.far)) + fabsf(rgd.ga);
+    if constexpr (DUAL) qmax += fabsf(rgd.gcd[0]) + fabsf(rgd.gcd[1]) + fabsf(rgd.gcd[2]);
     alive = s.i_lo <= s.i_hi;
   }
   const bool diffuse = (c.flags & R3D_FLAG_DIFFUSE) != 0;
@@ -1001,6 +1045,7 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_BWD_BLOCKS) render_bwd
     float wc[8];
     int vox[8];
     float draw[3] = {0.f, 0.f, 0.f}, dpre = 0.f;
+    float draw0[3] = {0.f, 0.f, 0.f};  // DUAL: d L / d raw_diffuse, lands on the k = 0 coefficients only
     unsigned long long key = 0ull;  // 64-bit: voxel offset (up to 2^31) + the low corner's validity pattern
     if (alive && i >= s.i_lo && i <= s.i_hi) {
       if (!have_z) dm.start(s.dg, i), z = dm.next(s.dg, i), have_z = true;
@@ -1028,7 +1073,19 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_BWD_BLOCKS) render_bwd
             gather_radiance<DEG, VEC>(g, cell, Y, diffuse, rr, rg, rb);
             sr = sigmoidf_(rr), sg = sigmoidf_(rg), sb = sigmoidf_(rb);
           }
-          const float q = fmaf(rgd.gc[0], sr, fmaf(rgd.gc[1], sg, fmaf(rgd.gc[2], sb, fmaf(rgd.gd, z, rgd.ga))));
+          float q = fmaf(rgd.gc[0], sr, fmaf(rgd.gc[1], sg, fmaf(rgd.gc[2], sb, fmaf(rgd.gd, z, rgd.ga))));
+          float dr = 0.f, dg_ = 0.f, db = 0.f;  // band-0 radiance of the sample (DUAL)
+          if constexpr (DUAL) {
+            if (b.cache_diffuse && sigma != 0.0f) {
+              const float4 cd = __ldg(b.cache_diffuse + (size_t)i * rp.n + ray);
+              dr = cd.x, dg_ = cd.y, db = cd.z;
+            } else {
+              float rr, rg, rb;
+              gather_radiance<DEG, VEC>(g, cell, Y, true, rr, rg, rb);
+              dr = sigmoidf_(rr), dg_ = sigmoidf_(rg), db = sigmoidf_(rb);
+            }
+            q = fmaf(rgd.gcd[0], dr, fmaf(rgd.gcd[1], dg_, fmaf(rgd.gcd[2], db, q)));
+          }
           prefix = fmaf(w, q, prefix);
           float suffix = 0.0f;  // see render_bwd_kernel for the clamp
           if (!last && Tn != 0.0f) {
@@ -1041,8 +1098,14 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_BWD_BLOCKS) render_bwd
             draw[0] = w * rgd.gc[0] * sr * (1.0f - sr);
             draw[1] = w * rgd.gc[1] * sg * (1.0f - sg);
             draw[2] = w * rgd.gc[2] * sb * (1.0f - sb);
+            if constexpr (DUAL) {
+              draw0[0] = w * rgd.gcd[0] * dr * (1.0f - dr);
+              draw0[1] = w * rgd.gcd[1] * dg_ * (1.0f - dg_);
+              draw0[2] = w * rgd.gcd[2] * db * (1.0f - db);
+            }
           }
           contributes = (dpre != 0.f) || (draw[0] != 0.f) || (draw[1] != 0.f) || (draw[2] != 0.f);
+          if constexpr (DUAL) contributes = contributes || (draw0[0] != 0.f) || (draw0[1] != 0.f) || (draw0[2] != 0.f);
           if (contributes) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
@@ -1074,6 +1137,7 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_BWD_BLOCKS) render_bwd
           const int e = 4 * j + l;
           const bool on = (e < F) && (!(DEG > 0 && diffuse) || (e % K) == 0);
           q4[l] = on ? draw[e / K] * Y[e % K] : 0.0f;
+          if (DUAL && e < F && (e % K) == 0) q4[l] = (draw[e / K] + draw0[e / K]) * Y[0];
         }
         *reinterpret_cast<float4*>(Prow + 4 * j) = make_float4(q4[0], q4[1], q4[2], q4[3]);
       }
@@ -1193,11 +1257,11 @@ static void launch_fwd(int vec, int variant, dim3 grid, cudaStream_t st, const G
       static const int carve = [] {
         const char* e = getenv("R3D_FWD_CARVEOUT");
         const int v = e ? atoi(e) : -1;
-        if (v >= 0) cudaFuncSetAttribute(render_fwd_group_kernel<DEG>, cudaFuncAttributePreferredSharedMemoryCarveout, v);
+        if (v >= 0) cudaFuncSetAttribute(render_fwd_group_kernel<DEG, false>, cudaFuncAttributePreferredSharedMemoryCarveout, v);
         return v;
       }();
       (void)carve;
-      render_fwd_group_kernel<DEG><<<grid, 128, 0, st>>>(g, r, c, o);
+      render_fwd_group_kernel<DEG, false><<<grid, 128, 0, st>>>(g, r, c, o);
     }
     return;
   }
@@ -1220,11 +1284,28 @@ static void launch_bwd(int vec, int variant, dim3 grid, cudaStream_t st, const G
     return;
   }
   if (vec == 8)
-    render_bwd_coop_kernel<DEG, 8><<<grid, 128, 0, st>>>(g, r, c, b);
+    render_bwd_coop_kernel<DEG, 8, false><<<grid, 128, 0, st>>>(g, r, c, b);
   else if (vec == 4)
-    render_bwd_coop_kernel<DEG, 4><<<grid, 128, 0, st>>>(g, r, c, b);
+    render_bwd_coop_kernel<DEG, 4, false><<<grid, 128, 0, st>>>(g, r, c, b);
   else
-    render_bwd_coop_kernel<DEG, 0><<<grid, 128, 0, st>>>(g, r, c, b);
+    render_bwd_coop_kernel<DEG, 0, false><<<grid, 128, 0, st>>>(g, r, c, b);
+}
+
+// The single-pass specular + diffuse render exists in the lane-group forward and the cooperative backward only.
+static bool dual_supported(const GridP& g, const CfgP& c, int vec) {
+  return vec != 0 && !(c.flags & R3D_FLAG_DIFFUSE) &&
+         (unsigned long long)g.W * g.D * g.H * (unsigned long long)(g.stride / 4) <= 0xffffffffull;
+}
+template <int DEG>
+static void launch_fwd_dual(dim3 grid, cudaStream_t st, const GridP& g, const RaysP& r, const CfgP& c, const OutP& o) {
+  render_fwd_group_kernel<DEG, true><<<grid, 128, 0, st>>>(g, r, c, o);
+}
+template <int DEG>
+static void launch_bwd_dual(int vec, dim3 grid, cudaStream_t st, const GridP& g, const RaysP& r, const CfgP& c, const BwdP& b) {
+  if (vec == 8)
+    render_bwd_coop_kernel<DEG, 8, true><<<grid, 128, 0, st>>>(g, r, c, b);
+  else
+    render_bwd_coop_kernel<DEG, 4, true><<<grid, 128, 0, st>>>(g, r, c, b);
 }
 
 // widest vector access the feature layout allows: 8 floats (256-bit loads; records are whole 32-byte sectors),
@@ -1258,12 +1339,27 @@ extern "C" int r3d_render_fwd(const R3dGrid* grid, const R3dRays* rays, const R3
   if ((rc = to_device_params(grid, g)) || (rc = to_device_params(rays, r)) || (rc = to_device_params(cfg, r, c))) return rc;
   if (r.n == 0) return R3D_OK;
   if (!out || !out->colour || !out->depth || !out->acc) return fail(R3D_ERR_INVALID_ARGUMENT, "render output buffers are NULL");
-  OutP o{out->colour, out->depth, out->acc, out->disparity, reinterpret_cast<float4*>(out->sample_cache)};
-  if (o.cache && !aligned16(o.cache)) return fail(R3D_ERR_INVALID_ARGUMENT, "sample_cache must be 16-byte aligned");
+  OutP o{out->colour, out->depth, out->acc, out->disparity, reinterpret_cast<float4*>(out->sample_cache),
+         out->colour_diffuse, reinterpret_cast<float4*>(out->sample_cache_diffuse)};
+  if ((o.cache && !aligned16(o.cache)) || (o.cache_diffuse && !aligned16(o.cache_diffuse)))
+    return fail(R3D_ERR_INVALID_ARGUMENT, "sample_cache must be 16-byte aligned");
   dim3 blocks;
   if ((rc = grid_blocks(r, blocks))) return rc;
   const int vec = vector_width(g, nullptr);
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  if (o.colour_diffuse) {  // single-pass specular + diffuse render
+    if (!dual_supported(g, c, vec))
+      return fail(R3D_ERR_UNSUPPORTED, "colour_diffuse (single-pass specular + diffuse render) needs a 16-byte aligned feature layout "
+                                       "with a stride that is a multiple of 4 floats, and R3D_FLAG_DIFFUSE clear");
+    switch (grid->sh_degree) {
+      case 0: launch_fwd_dual<0>(blocks, st, g, r, c, o); break;
+      case 1: launch_fwd_dual<1>(blocks, st, g, r, c, o); break;
+      case 2: launch_fwd_dual<2>(blocks, st, g, r, c, o); break;
+      default: launch_fwd_dual<3>(blocks, st, g, r, c, o); break;
+    }
+    return check_launch("r3d_render_fwd");
+  }
+  if (o.cache_diffuse) return fail(R3D_ERR_INVALID_ARGUMENT, "sample_cache_diffuse without colour_diffuse");
   switch (grid->sh_degree) {
     case 0: launch_fwd<0>(vec, cfg->variant, blocks, st, g, r, c, o); break;
     case 1: launch_fwd<1>(vec, cfg->variant, blocks, st, g, r, c, o); break;
@@ -1287,12 +1383,28 @@ extern "C" int r3d_render_bwd(const R3dGrid* grid, const R3dRays* rays, const R3
   if (!grad_grid->densities && !grad_grid->features) return R3D_OK;
   BwdP b{saved->colour,   saved->depth,        saved->acc,           grad_out->colour,     grad_out->depth,
          grad_out->acc,   grad_out->disparity, grad_grid->densities, grad_grid->features,
-         reinterpret_cast<const float4*>(saved->sample_cache)};
-  if (b.cache && !aligned16(b.cache)) return fail(R3D_ERR_INVALID_ARGUMENT, "sample_cache must be 16-byte aligned");
+         reinterpret_cast<const float4*>(saved->sample_cache),
+         saved->colour_diffuse, grad_out->colour_diffuse, reinterpret_cast<const float4*>(saved->sample_cache_diffuse)};
+  if ((b.cache && !aligned16(b.cache)) || (b.cache_diffuse && !aligned16(b.cache_diffuse)))
+    return fail(R3D_ERR_INVALID_ARGUMENT, "sample_cache must be 16-byte aligned");
   dim3 blocks;
   if ((rc = grid_blocks(r, blocks))) return rc;
   const int vec = vector_width(g, b.gfeat);
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  if (b.g_colour_diffuse) {  // backward of the single-pass specular + diffuse render
+    if (!b.colour_diffuse) return fail(R3D_ERR_INVALID_ARGUMENT, "grad_out.colour_diffuse needs the saved colour_diffuse of the forward call");
+    if (!dual_supported(g, c, vec))
+      return fail(R3D_ERR_UNSUPPORTED, "colour_diffuse gradients need a 16-byte aligned feature / gradient layout with a stride that is a "
+                                       "multiple of 4 floats, and R3D_FLAG_DIFFUSE clear");
+    switch (grid->sh_degree) {
+      case 0: launch_bwd_dual<0>(vec, blocks, st, g, r, c, b); break;
+      case 1: launch_bwd_dual<1>(vec, blocks, st, g, r, c, b); break;
+      case 2: launch_bwd_dual<2>(vec, blocks, st, g, r, c, b); break;
+      default: launch_bwd_dual<3>(vec, blocks, st, g, r, c, b); break;
+    }
+    return check_launch("r3d_render_bwd");
+  }
+  b.colour_diffuse = nullptr, b.cache_diffuse = nullptr;  // no diffuse gradient: the plain kernels
   switch (grid->sh_degree) {
     case 0: launch_bwd<0>(vec, cfg->variant, blocks, st, g, r, c, b); break;
     case 1: launch_bwd<1>(vec, cfg->variant, blocks, st, g, r, c, b); break;

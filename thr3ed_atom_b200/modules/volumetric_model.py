@@ -30,6 +30,7 @@ from thr3ed_atom_b200.thre3d_reprs.renderers import (
     RenderProcedure,
     render_sh_voxel_grid,
     render_sh_voxel_grid_camera,
+    render_sh_voxel_grid_with_diffuse,
 )
 from thr3ed_atom_b200.utils.constants import EXTRA_INFO
 from thr3ed_atom_b200.utils.imaging_utils import CameraIntrinsics, CameraPose
@@ -84,6 +85,16 @@ class VolumetricModel:
         """Differentiable render of a flat ray batch; ``kwargs`` override render-config fields for this call only."""
         call_config = _with_overrides(self._render_config, kwargs)
         return self._render_procedure(self._thre3d_repr, rays, call_config, parallel_points_chunk_size)
+
+    def render_rays_with_diffuse(self, rays: Rays, parallel_points_chunk_size: Optional[int] = None, **kwargs) -> Tuple[RenderOut, RenderOut]:
+        """``(render_rays(rays), render_rays(rays, render_diffuse=True))`` from one fused march (the pair the reference
+        trainer computes with two calls, ``modules/trainers.py:306-330``); both images share the stratified sample
+        positions.  Other procedures than the fused SH voxel-grid renderer fall back to the two calls."""
+        call_config = _with_overrides(self._render_config, kwargs)
+        if self._render_procedure is render_sh_voxel_grid:
+            return render_sh_voxel_grid_with_diffuse(self._thre3d_repr, rays, call_config, parallel_points_chunk_size)
+        return (self._render_procedure(self._thre3d_repr, rays, call_config, parallel_points_chunk_size),
+                self._render_procedure(self._thre3d_repr, rays, _with_overrides(call_config, {"render_diffuse": True}), parallel_points_chunk_size))
 
     def render(
         self,

@@ -95,24 +95,33 @@ _direct_grad_targets = {}
 
 class _FusedSHVoxGridRender(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, densities: Tensor, features: Tensor, origins: Tensor, directions: Tensor, grid: VoxelGrid, args: _kernels.RenderArgs):
+    def forward(ctx, densities: Tensor, features: Tensor, origins: Tensor, directions: Tensor, grid: VoxelGrid, args: _kernels.RenderArgs,
+                with_diffuse: bool = False):
         desc = grid.kernel_desc(densities, features)
         # When a backward pass will follow, the forward keeps (sigmoid(raw) rgb, sigma) of every contributing sample
         # ([S, N, 4] fp32) so that the backward does not gather the 8 corner records a second time.
-        cache = None
+        cache = cache_d = None
         n = origins.shape[0]
         if (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]) and n > 0:
-            if _kernels.sample_cache_bytes(n, args.num_samples) <= sample_cache_limit_bytes():
+            if _kernels.sample_cache_bytes(n, args.num_samples) * (2 if with_diffuse else 1) <= sample_cache_limit_bytes():
                 cache = _kernels.new_sample_cache(n, args.num_samples, origins.device)
-        colour, depth, acc, disparity = _kernels.render_forward(desc, origins, directions, args, cache)
-        ctx.desc, ctx.args, ctx.cache = desc, args, cache
-        ctx.save_for_backward(origins, directions, colour, depth, acc)
+                cache_d = _kernels.new_sample_cache(n, args.num_samples, origins.device) if with_diffuse else None
+        ctx.desc, ctx.args, ctx.cache, ctx.cache_d, ctx.with_diffuse = desc, args, cache, cache_d, with_diffuse
         ctx.set_materialize_grads(False)  # unused outputs arrive as None instead of zero tensors
+        if with_diffuse:
+            colour, depth, acc, disparity, colour_d = _kernels.render_forward(desc, origins, directions, args, cache, True, cache_d)
+            ctx.save_for_backward(origins, directions, colour, depth, acc, colour_d)
+            return colour, depth, acc, disparity, colour_d
+        colour, depth, acc, disparity = _kernels.render_forward(desc, origins, directions, args, cache)
+        ctx.save_for_backward(origins, directions, colour, depth, acc)
         return colour, depth, acc, disparity
 
     @staticmethod
-    def backward(ctx, g_colour, g_depth, g_acc, g_disparity):
-        origins, directions, colour, depth, acc = ctx.saved_tensors
+    def backward(ctx, g_colour, g_depth, g_acc, g_disparity, g_colour_d=None):
+        if ctx.with_diffuse:
+            origins, directions, colour, depth, acc, colour_d = ctx.saved_tensors
+        else:
+            (origins, directions, colour, depth, acc), colour_d = ctx.saved_tensors, None
         desc = ctx.desc
         need_d, need_f = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         direct_d = _direct_grad_targets.get(desc.densities.data_ptr()) if need_d else None
@@ -122,11 +131,11 @@ class _FusedSHVoxGridRender(torch.autograd.Function):
         if need_d or need_f:
             _kernels.render_backward(
                 desc, origins, directions, ctx.args, (colour, depth, acc), (g_colour, g_depth, g_acc, g_disparity), grad_d, grad_f,
-                ctx.cache,
+                ctx.cache, diffuse=(colour_d, g_colour_d, ctx.cache_d) if (ctx.with_diffuse and g_colour_d is not None) else None,
             )
-        ctx.cache = None  # free the per-sample records as soon as they are consumed
+        ctx.cache = ctx.cache_d = None  # free the per-sample records as soon as they are consumed
         # gradients accumulated into a registered target are already where they belong
-        return (None if direct_d is not None else grad_d), (None if direct_f is not None else grad_f), None, None, None, None
+        return (None if direct_d is not None else grad_d), (None if direct_f is not None else grad_f), None, None, None, None, None
 
 
 def sample_cache_limit_bytes() -> int:
@@ -201,6 +210,40 @@ def render_sh_voxel_grid(
         voxel_grid.densities, voxel_grid.feature_storage, origins, directions, voxel_grid, args
     )
     return RenderOut(colour=colour, depth=depth, extra={EXTRA_DISPARITY: disparity, EXTRA_ACCUMULATED_WEIGHTS: acc})
+
+
+def render_sh_voxel_grid_with_diffuse(
+    voxel_grid: VoxelGrid,
+    rays: Rays,
+    render_config: SHVoxGridRenderConfig,
+    parallel_points_chunk_size: Optional[int] = None,
+) -> Tuple[RenderOut, RenderOut]:
+    """Single-pass specular + diffuse render.
+
+    The reference trainer renders every ray batch twice -- ``vol_mod.render_rays(rays)`` and
+    ``vol_mod.render_rays(rays, render_diffuse=True)`` (``modules/trainers.py:306-330``) -- to regularise the geometry with
+    the view-independent image.  The diffuse radiance is ``C0 * coeff[ch][0]`` (``process.py:59-63``): the ``k = 0`` element
+    of the very voxel records the specular render gathers.  This call produces both images from ONE march, ONE 8-corner
+    gather per sample and ONE backward pass.  Returns ``(specular RenderOut, diffuse RenderOut)``; depth, disparity and
+    accumulated weight are shared (they do not depend on the radiance).
+
+    Semantic difference to two reference calls: both images see the SAME stratified sample positions (the reference draws
+    a fresh ``torch.rand`` for each render); with ``perturb_sampled_points=False`` the results are identical.
+    ``render_config.render_diffuse`` must be False."""
+    assert_flat_rays(rays)
+    _validate_config(render_config)
+    if render_config.render_diffuse:
+        raise ValueError("render_sh_voxel_grid_with_diffuse renders both images; render_config.render_diffuse must be False")
+    args = make_render_args(render_config)
+    if args.image_hw is not None and args.image_hw[0] * args.image_hw[1] != rays.origins.shape[0]:
+        args.image_hw = None
+    origins = rays.origins.detach().contiguous()
+    directions = rays.directions.detach().contiguous()
+    colour, depth, acc, disparity, colour_d = _FusedSHVoxGridRender.apply(
+        voxel_grid.densities, voxel_grid.feature_storage, origins, directions, voxel_grid, args, True
+    )
+    extra = {EXTRA_DISPARITY: disparity, EXTRA_ACCUMULATED_WEIGHTS: acc}
+    return RenderOut(colour=colour, depth=depth, extra=extra), RenderOut(colour=colour_d, depth=depth, extra=dict(extra))
 
 
 def render_sh_voxel_grid_camera(voxel_grid: VoxelGrid, camera_intrinsics, camera_pose, render_config: SHVoxGridRenderConfig) -> RenderOut:
