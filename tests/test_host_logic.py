@@ -213,6 +213,27 @@ def test_rendering_cpu_tensors_is_refused_not_emulated():
         render_sh_voxel_grid(grid, Rays(torch.zeros(2, 2, 3), torch.ones(2, 2, 3)), SHVoxGridRenderConfig(8, CameraBounds(1.0, 2.0)))
 
 
+def test_single_pass_specular_and_diffuse_render_host_contract():
+    """render_sh_voxel_grid_with_diffuse: same refusals as the single render (no CPU emulation, flat rays), the config
+    must not ask for a diffuse-only render, VolumetricModel forwards config overrides and rejects unknown ones."""
+    from thr3ed_atom_b200.thre3d_reprs.renderers import render_sh_voxel_grid_with_diffuse
+
+    grid = _grid(2)
+    rays = Rays(torch.zeros(5, 3), torch.ones(5, 3))
+    cfg = SHVoxGridRenderConfig(8, CameraBounds(1.0, 2.0))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        render_sh_voxel_grid_with_diffuse(grid, rays, cfg)
+    with pytest.raises(ValueError, match="render_diffuse must be False"):
+        render_sh_voxel_grid_with_diffuse(grid, rays, SHVoxGridRenderConfig(8, CameraBounds(1.0, 2.0), render_diffuse=True))
+    with pytest.raises(AssertionError, match="FLAT RAYS"):
+        render_sh_voxel_grid_with_diffuse(grid, Rays(torch.zeros(2, 2, 3), torch.ones(2, 2, 3)), cfg)
+    vol_mod = VolumetricModel(grid, render_sh_voxel_grid, cfg, device=torch.device("cpu"))
+    with pytest.raises(ValueError, match="Unknown render configuration field"):
+        vol_mod.render_rays_with_diffuse(rays, not_a_field=3)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        vol_mod.render_rays_with_diffuse(rays, num_samples_per_ray=4)
+
+
 # ---------------------------------------------------------------------------- ray / output glue, cameras
 def test_ray_and_output_containers():
     rays = Rays(torch.arange(24.0).reshape(2, 4, 3), torch.ones(2, 4, 3))
