@@ -47,6 +47,11 @@
 #ifndef R3D_BWD_BLOCKS
 #define R3D_BWD_BLOCKS 5
 #endif
+// backward of the single-pass specular + diffuse render: at 5 CTAs/SM (96 registers) it spills 172 bytes; measured
+// 12.52 vs 12.90 ms (c3 step) and 3.07 vs 3.29 ms (32768-ray trainer step) in favour of 4 CTAs/SM (128 registers)
+#ifndef R3D_BWD_DUAL_BLOCKS
+#define R3D_BWD_DUAL_BLOCKS 4
+#endif
 
 namespace r3d {
 
@@ -654,7 +659,7 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_FWD_BLOCKS) render_fwd
       if (inside_aabb(g, px, py, pz)) {
         make_cell_inside(g, px, py, pz, cell);
         float dpost;
-        sigma = density_post(g.post, density_pre_interp(g, cell), dpost);
+        sigma = density_post(g.post, density_pre_interp<true>(g, cell), dpost);
         contributes = sigma != 0.0f;
       }
     }
@@ -989,7 +994,7 @@ struct alignas(16) CoopSmem {
 // DUAL: backward of the single-pass specular + diffuse render: the band-0 image adds g_cd . sigmoid(raw_d_i) to q_i and
 // d raw_d[ch] * Y[0] to element ch * K of the product row; nothing else changes (same samples, same weights).
 template <int DEG, int VEC, bool DUAL>
-__global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_BWD_BLOCKS) render_bwd_coop_kernel(const GridP g, const RaysP rp, const CfgP c, const BwdP b) {
+__global__ void __launch_bounds__(128, DEG >= 3 ? 3 : (DUAL ? R3D_BWD_DUAL_BLOCKS : R3D_BWD_BLOCKS)) render_bwd_coop_kernel(const GridP g, const RaysP rp, const CfgP c, const BwdP b) {
   using S = CoopShape<DEG>;
   constexpr int K = S::K, F = S::F;
   constexpr unsigned FULL = 0xffffffffu;
