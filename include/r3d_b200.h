@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define R3D_ABI_VERSION 3
+#define R3D_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define R3D_API __attribute__((visibility("default")))
@@ -123,6 +123,12 @@ typedef struct R3dRenderOut {
    * depth, acc and disparity are common to both (they do not depend on the radiance). */
   float* colour_diffuse;        /* [N][3], optional */
   float* sample_cache_diffuse;  /* optional [S][N][4] like sample_cache: (sigmoid(raw_diffuse) rgb, -) per sample */
+  /* Optional [S][r3d_sample_mask_words(rays)] uint32, with sample_cache.  Forward: word [sample][warp] = ballot of the warp's
+   * rays whose sample contributed (sigma != 0); written by the default (lane-group) forward kernel only -- r3d_render_fwd
+   * fails with R3D_ERR_UNSUPPORTED if another kernel would be dispatched.  Backward (`saved`): with a ReLU density
+   * post-activation the march then needs neither the inside test nor the 8-corner density gather (sigma comes from
+   * sample_cache), and marching steps in which no ray of a warp contributed are skipped outright. */
+  uint32_t* sample_mask;
 } R3dRenderOut;
 
 /* upstream gradients dL/d(output); any pointer may be NULL (= zero). */
@@ -141,6 +147,8 @@ typedef struct R3dGridGrad {
 } R3dGridGrad;
 
 R3D_API int r3d_abi_version(void);
+/* words per sample of R3dRenderOut.sample_mask for this ray batch (= warps of the render launch) */
+R3D_API int64_t r3d_sample_mask_words(const R3dRays* rays);
 R3D_API const char* r3d_last_error(void);
 
 /* Forward: replaces render_sh_voxel_grid (thre3d_reprs/renderers.py:48-102) =

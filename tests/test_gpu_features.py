@@ -541,3 +541,53 @@ def test_many_samples_per_ray_and_non_contiguous_ray_views(cuda_device):
            "acc": out.extra["accumulated_weight"].detach().cpu().numpy(), "disparity": out.extra["disparity"].detach().cpu().numpy()}
     assert_outputs_close(got, want, atol=1e-5, rtol_depth=1e-5, what="s1024")
     assert rel_l2(grid.feature_storage.grad[..., :27].cpu().numpy(), want["grad_features"]) < 5e-5
+
+
+# ---------------------------------------------------------------------------------------------
+# backward marching by the forward's contribution ballots (R3dRenderOut.sample_mask)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["deg2_16cube", "deg2_jitter", "deg2_sparse", "c1_32cube_deg0", "deg2_random_rays", "deg3_abs", "deg1_aniso_softplus"])
+def test_backward_by_contribution_ballots_equals_the_density_march(name, cuda_device, monkeypatch):
+    """With a ReLU field the backward takes sigma from the forward's per-sample records and the set of contributing samples
+    from its per-step ballots instead of repeating the inside test and the density gather: same samples, same sigma bits =>
+    same gradients up to the order of the atomic sums.  Other post-activations keep the density march (the mask is then
+    not even allocated); both are compared with R3D_SAMPLE_MASK=0."""
+    from thr3ed_atom_b200 import _kernels
+    from thr3ed_atom_b200.thre3d_reprs.renderers import make_render_args
+
+    case = CASES[name]
+    inp = build_inputs(case)
+    res = {}
+    for label, env in (("mask", "1"), ("march", "0")):
+        monkeypatch.setenv("R3D_SAMPLE_MASK", env)
+        res[label] = run_cuda_case(case, inp, cuda_device, with_grads=True, use_tile_hint=True)
+    for key in ("colour", "depth", "acc"):
+        assert np.array_equal(res["mask"][key], res["march"][key]), key
+    assert rel_l2(res["mask"]["grad_features"], res["march"]["grad_features"]) < 1e-6
+    assert rel_l2(res["mask"]["grad_densities"], res["march"]["grad_densities"]) < 1e-6
+    grid = make_cuda_grid(case, inp, cuda_device)
+    expect = case.density_post == "relu" and not case.diffuse
+    assert _kernels.sample_mask_supported(grid.kernel_desc(), make_render_args(make_cuda_config(case))) == expect
+
+
+def test_sample_mask_is_refused_when_another_forward_kernel_would_run(cuda_device):
+    """The library never accepts a mask it would not write (per-ray / staged forward variants)."""
+    from thr3ed_atom_b200 import _kernels
+    from thr3ed_atom_b200.thre3d_reprs.renderers import make_render_args
+
+    case = CASES["deg2_16cube"]
+    inp = build_inputs(case)
+    grid = make_cuda_grid(case, inp, cuda_device)
+    desc = grid.kernel_desc()
+    o, d = torch.from_numpy(inp["origins"]).to(cuda_device), torch.from_numpy(inp["directions"]).to(cuda_device)
+    args = make_render_args(make_cuda_config(case))
+    cache = _kernels.new_sample_cache(o.shape[0], args.num_samples, cuda_device)
+    mask = _kernels.new_sample_mask(desc, o, d, o.shape[0], args)
+    assert mask.shape == (args.num_samples, (o.shape[0] + 127) // 128 * 4)
+    _kernels.render_forward(desc, o, d, args, cache, sample_mask=mask)  # default kernel: accepted
+    args.variant = 8
+    with pytest.raises(RuntimeError, match="sample_mask needs"):
+        _kernels.render_forward(desc, o, d, args, cache, sample_mask=mask)
+    args.variant = 0
+    with pytest.raises(RuntimeError, match="sample_mask needs"):
+        _kernels.render_forward(desc, o, d, args, None, sample_mask=mask)

@@ -13,7 +13,7 @@ from typing import Optional
 
 # $R3D_LIB_PATH selects another build of the same library (tuning experiments: other -D flags); default = the in-tree build
 LIB_PATH = Path(os.environ.get("R3D_LIB_PATH") or (Path(__file__).resolve().parent / "_lib" / "libr3d_b200.so"))
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # enums of r3d_b200.h
 PRE_IDENTITY, PRE_ABS = 0, 1
@@ -77,7 +77,7 @@ class R3dRenderConfig(C.Structure):
 
 class R3dRenderOut(C.Structure):
     _fields_ = [("colour", C.c_void_p), ("depth", C.c_void_p), ("acc", C.c_void_p), ("disparity", C.c_void_p), ("sample_cache", C.c_void_p),
-                ("colour_diffuse", C.c_void_p), ("sample_cache_diffuse", C.c_void_p)]
+                ("colour_diffuse", C.c_void_p), ("sample_cache_diffuse", C.c_void_p), ("sample_mask", C.c_void_p)]
 
 
 class R3dRenderOutGrad(C.Structure):
@@ -92,6 +92,7 @@ class R3dGridGrad(C.Structure):
 SIGNATURES = {
     "r3d_abi_version": (C.c_int, []),
     "r3d_last_error": (C.c_char_p, []),
+    "r3d_sample_mask_words": (C.c_int64, [C.POINTER(R3dRays)]),
     "r3d_render_fwd": (C.c_int, [C.POINTER(R3dGrid), C.POINTER(R3dRays), C.POINTER(R3dRenderConfig), C.POINTER(R3dRenderOut), C.c_void_p]),
     "r3d_render_bwd": (
         C.c_int,

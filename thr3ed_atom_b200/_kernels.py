@@ -151,8 +151,28 @@ def new_sample_cache(num_rays: int, num_samples: int, device) -> Tensor:
     return torch.empty((num_samples, num_rays, 4), dtype=torch.float32, device=device)
 
 
+def sample_mask_supported(grid: GridDesc, args: RenderArgs) -> bool:
+    """Will ``render_forward`` dispatch the lane-group kernel (the one that writes the per-step contribution ballots), and can
+    the backward use them (ReLU density post-activation)?  Mirrors ``fwd_uses_group_kernel`` / ``mask_usable`` in
+    ``csrc/r3d_render.cu``; the library refuses a mask it would not write."""
+    f = grid.features
+    return (args.variant == 0 and not args.diffuse and grid.density_post == _abi.POST_RELU and f.shape[3] % 4 == 0
+            and f.data_ptr() % 16 == 0 and f.shape[0] * f.shape[1] * f.shape[2] * (f.shape[3] // 4) <= 0xFFFFFFFF)
+
+
+def new_sample_mask(grid: GridDesc, origins: Optional[Tensor], directions: Optional[Tensor], num_rays: int, args: RenderArgs) -> Tensor:
+    """Uninitialised ``[S, warps]`` int32 buffer for the forward's per-step contribution ballots."""
+    _, r, _, keep = _pack_call(grid, origins, directions, num_rays, args)
+    words = int(_abi.lib().r3d_sample_mask_words(C.byref(r)))
+    del keep
+    if words < 0:
+        _abi.check(1, "r3d_sample_mask_words")
+    return torch.empty((args.num_samples, words), dtype=torch.int32, device=grid.features.device)
+
+
 def render_forward(grid: GridDesc, origins: Optional[Tensor], directions: Optional[Tensor], args: RenderArgs,
-                   sample_cache: Optional[Tensor] = None, with_diffuse: bool = False, sample_cache_diffuse: Optional[Tensor] = None):
+                   sample_cache: Optional[Tensor] = None, with_diffuse: bool = False, sample_cache_diffuse: Optional[Tensor] = None,
+                   sample_mask: Optional[Tensor] = None):
     """Fused forward render.  Returns ``(colour [N,3], depth [N,1], acc [N,1], disparity [N,1])``.
     ``sample_cache`` (``new_sample_cache``) is filled for the backward pass when given.
     ``with_diffuse``: single-pass specular + diffuse render -- a fifth return value ``colour_diffuse [N,3]`` is the band-0
@@ -174,7 +194,7 @@ def render_forward(grid: GridDesc, origins: Optional[Tensor], directions: Option
         if not with_diffuse or tuple(sample_cache_diffuse.shape) != (args.num_samples, n, 4) or not sample_cache_diffuse.is_contiguous():
             raise ValueError(f"sample_cache_diffuse needs with_diffuse and a contiguous [{args.num_samples}, {n}, 4] tensor")
     out = _abi.R3dRenderOut(colour.data_ptr(), depth.data_ptr(), acc.data_ptr(), disparity.data_ptr(), _ptr(sample_cache),
-                            _ptr(colour_diffuse), _ptr(sample_cache_diffuse))
+                            _ptr(colour_diffuse), _ptr(sample_cache_diffuse), _ptr(sample_mask))
     with torch.cuda.device(device):
         _abi.check(_abi.lib().r3d_render_fwd(C.byref(g), C.byref(r), C.byref(c), C.byref(out), _stream(device)), "r3d_render_fwd")
     del keep
@@ -194,6 +214,7 @@ def render_backward(
     grad_features: Optional[Tensor],
     sample_cache: Optional[Tensor] = None,
     diffuse: Optional[Tuple[Tensor, Optional[Tensor], Optional[Tensor]]] = None,
+    sample_mask: Optional[Tensor] = None,
 ) -> None:
     """Fused backward: accumulates into ``grad_densities`` / ``grad_features`` (same layout as the grid).
     ``sample_cache`` must be the buffer the matching forward call filled (else the radiance is re-gathered).
@@ -205,7 +226,8 @@ def render_backward(
     colour_d, grad_colour_d, cache_d = diffuse if diffuse is not None else (None, None, None)
     if grad_colour_d is not None:
         grad_colour_d = _require_cuda(grad_colour_d.contiguous(), "grad_output")
-    sv = _abi.R3dRenderOut(colour.data_ptr(), depth.data_ptr(), acc.data_ptr(), None, _ptr(sample_cache), _ptr(colour_d), _ptr(cache_d))
+    sv = _abi.R3dRenderOut(colour.data_ptr(), depth.data_ptr(), acc.data_ptr(), None, _ptr(sample_cache), _ptr(colour_d), _ptr(cache_d),
+                           _ptr(sample_mask))
     gs = [None if t is None else _require_cuda(t.contiguous(), "grad_output") for t in grads]
     go = _abi.R3dRenderOutGrad(*[_ptr(t) for t in gs], _ptr(grad_colour_d))
     for t, ref in ((grad_densities, grid.densities), (grad_features, grid.features)):

@@ -63,6 +63,7 @@ struct OutP {
   float4* __restrict__ cache;  // optional [S][N] (sigmoid(raw) rgb, sigma) of every sigma != 0 sample, for the backward
   float* __restrict__ colour_diffuse;  // single-pass specular + diffuse render: band-0 image of the same samples
   float4* __restrict__ cache_diffuse;  // optional [S][N] (sigmoid(raw_diffuse) rgb, -)
+  unsigned* __restrict__ mask;         // optional [S][warps of the launch]: ballot of the contributing rays per marching step
 };
 
 struct BwdP {
@@ -79,6 +80,7 @@ struct BwdP {
   const float* __restrict__ colour_diffuse;    // single-pass specular + diffuse render: saved band-0 image,
   const float* __restrict__ g_colour_diffuse;  //   its upstream gradient (nullable)
   const float4* __restrict__ cache_diffuse;    //   and its per-sample records
+  const unsigned* __restrict__ mask;           // optional contribution ballots written by the forward (see OutP)
 };
 
 struct RayCtx {
@@ -664,6 +666,7 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_FWD_BLOCKS) render_fwd
       }
     }
     const unsigned act = __ballot_sync(FULL, contributes);
+    if (out.mask && lane == 0) out.mask[(size_t)i * (gridDim.x * 4u) + (blockIdx.x * 4u + (threadIdx.x >> 5))] = act;
     if (act != 0u) {
       const int total = __popc(act);
       const int rank = __popc(act & ((1u << lane) - 1u));
@@ -993,7 +996,11 @@ struct alignas(16) CoopSmem {
 
 // DUAL: backward of the single-pass specular + diffuse render: the band-0 image adds g_cd . sigmoid(raw_d_i) to q_i and
 // d raw_d[ch] * Y[0] to element ch * K of the product row; nothing else changes (same samples, same weights).
-template <int DEG, int VEC, bool DUAL>
+// MASK: the forward left its per-step contribution ballots (BwdP::mask) and per-sample records (BwdP::cache, which hold
+// sigma) and the density post-activation is ReLU (d sigma / d pre = 1 wherever sigma != 0): a sample contributes to the
+// gradient exactly if it contributed to the image, so the march takes sigma from the cache and needs neither the inside test
+// nor the 8-corner density gather, and steps in which no ray of the warp contributed are skipped outright.
+template <int DEG, int VEC, bool DUAL, bool MASK>
 __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : (DUAL ? R3D_BWD_DUAL_BLOCKS : R3D_BWD_BLOCKS)) render_bwd_coop_kernel(const GridP g, const RaysP rp, const CfgP c, const BwdP b) {
   using S = CoopShape<DEG>;
   constexpr int K = S::K, F = S::F;
@@ -1038,6 +1045,11 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : (DUAL ? R3D_BWD_DUAL_BLOCK
   // in a band-0-only (diffuse) render only the float4s holding a k = 0 coefficient (elements 0, K, 2K) carry gradient
   const bool band_ok = !(DEG > 0 && diffuse) || (cj == 0) || (cj == K / 4) || (cj == (2 * K) / 4);
   const unsigned ustride = (unsigned)g.stride;
+  const unsigned mask_stride = gridDim.x * 4u, mask_warp = blockIdx.x * 4u + (threadIdx.x >> 5);
+  unsigned fmask_next = 0u;
+  if constexpr (MASK) {
+    if (lo <= hi) fmask_next = __ldg(b.mask + (size_t)lo * mask_stride + mask_warp);
+  }
 
   float T = 1.0f, prefix = 0.f;
   float z = 0.f;
@@ -1052,6 +1064,11 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : (DUAL ? R3D_BWD_DUAL_BLOCK
     float draw[3] = {0.f, 0.f, 0.f}, dpre = 0.f;
     float draw0[3] = {0.f, 0.f, 0.f};  // DUAL: d L / d raw_diffuse, lands on the k = 0 coefficients only
     unsigned long long key = 0ull;  // 64-bit: voxel offset (up to 2^31) + the low corner's validity pattern
+    unsigned fmask = 0u;
+    if constexpr (MASK) {
+      fmask = fmask_next;
+      if (i < hi) fmask_next = __ldg(b.mask + (size_t)(i + 1) * mask_stride + mask_warp);
+    }
     if (alive && i >= s.i_lo && i <= s.i_hi) {
       if (!have_z) dm.start(s.dg, i), z = dm.next(s.dg, i), have_z = true;
       const bool last = (i == c.S - 1);
@@ -1059,19 +1076,25 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : (DUAL ? R3D_BWD_DUAL_BLOCK
       const float px = __fadd_rn(r.ox, __fmul_rn(r.dx, z));
       const float py = __fadd_rn(r.oy, __fmul_rn(r.dy, z));
       const float pz = __fadd_rn(r.oz, __fmul_rn(r.dz, z));
-      if (inside_aabb(g, px, py, pz)) {
+      if (MASK ? ((fmask >> lane) & 1u) != 0u : inside_aabb(g, px, py, pz)) {
         Cell cell;
         make_cell_inside(g, px, py, pz, cell);
-        float dpost;
-        const float sigma = density_post(g.post, density_pre_interp(g, cell), dpost);
+        float dpost, sigma;
+        float4 cv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if constexpr (MASK) {
+          cv = __ldg(b.cache + (size_t)i * rp.n + ray);
+          sigma = cv.w, dpost = 1.0f;  // ReLU with sigma != 0
+        } else {
+          sigma = density_post(g.post, density_pre_interp(g, cell), dpost);
+        }
         if (sigma != 0.0f || dpost != 0.0f) {
           const float delta = last ? __fmul_rn(kInfinity, s.dnorm) : __fmul_rn(__fsub_rn(zn, z), s.dnorm);
           const float alpha = 1.0f - exp_neg(sigma * delta);
           const float w = alpha * T;
           const float Tn = T * (1.0f - alpha);
           float sr, sg, sb;
-          if (b.cache && sigma != 0.0f) {  // written by the forward for exactly the sigma != 0 samples
-            const float4 cv = __ldg(b.cache + (size_t)i * rp.n + ray);
+          if (MASK || (b.cache && sigma != 0.0f)) {  // written by the forward for exactly the sigma != 0 samples
+            if constexpr (!MASK) cv = __ldg(b.cache + (size_t)i * rp.n + ray);
             sr = cv.x, sg = cv.y, sb = cv.z;
           } else {
             float rr, rg, rb;
@@ -1245,6 +1268,21 @@ __global__ void __launch_bounds__(128) mark_touched_kernel(const GridP g, const 
 // =================================================================================================
 // host-side dispatch
 // =================================================================================================
+// the lane-group forward addresses records with 32-bit float4 indices
+static bool group_indexable(const GridP& g) {
+  return (unsigned long long)g.W * g.D * g.H * (unsigned long long)(g.stride / 4) <= 0xffffffffull;
+}
+// does r3d_render_fwd dispatch the lane-group kernel (the one that writes OutP::mask) for these arguments?
+static bool fwd_uses_group_kernel(const GridP& g, const CfgP& c, int vec, int variant, int sh_degree) {
+  const bool diffuse = (c.flags & R3D_FLAG_DIFFUSE) != 0 && sh_degree > 0;
+  return vec != 0 && !diffuse && !(variant & (2 | 4 | 8)) && group_indexable(g);
+}
+// the backward can march by the forward's contribution ballots when it also has the per-sample records (sigma) and the
+// density post-activation is ReLU (see render_bwd_coop_kernel)
+static bool mask_usable(const GridP& g, const BwdP& b, int vec) {
+  return b.mask != nullptr && b.cache != nullptr && vec != 0 && g.post == R3D_POST_RELU;
+}
+
 template <int DEG>
 static void launch_fwd(int vec, int variant, dim3 grid, cudaStream_t st, const GridP& g, const RaysP& r, const CfgP& c, const OutP& o) {
   // cooperative gather needs 16-byte aligned records; band-0-only (diffuse) renders read 3 floats per record and
@@ -1253,7 +1291,7 @@ static void launch_fwd(int vec, int variant, dim3 grid, cudaStream_t st, const G
   if (vec != 0 && !diffuse && !(variant & 2)) {
     if (variant & 4)  // TMA (cp.async.bulk) staging instead of per-lane cp.async: measured, see DESIGN.md
       render_fwd_coop_kernel<DEG, true><<<grid, 128, 0, st>>>(g, r, c, o);
-    else if ((variant & 8) || (unsigned long long)g.W * g.D * g.H * (unsigned long long)(g.stride / 4) > 0xffffffffull)
+    else if ((variant & 8) || !group_indexable(g))
       // shared-memory staged gather (the default before the lane-group kernel, which addresses records with 32-bit
       // float4 indices; no supported grid exceeds them: 512^3 at degree 3 is 1.6 G)
       render_fwd_coop_kernel<DEG, false><<<grid, 128, 0, st>>>(g, r, c, o);
@@ -1288,18 +1326,24 @@ static void launch_bwd(int vec, int variant, dim3 grid, cudaStream_t st, const G
       render_bwd_kernel<DEG, 0><<<grid, 128, 0, st>>>(g, r, c, b);
     return;
   }
+  if (mask_usable(g, b, vec)) {
+    if (vec == 8)
+      render_bwd_coop_kernel<DEG, 8, false, true><<<grid, 128, 0, st>>>(g, r, c, b);
+    else
+      render_bwd_coop_kernel<DEG, 4, false, true><<<grid, 128, 0, st>>>(g, r, c, b);
+    return;
+  }
   if (vec == 8)
-    render_bwd_coop_kernel<DEG, 8, false><<<grid, 128, 0, st>>>(g, r, c, b);
+    render_bwd_coop_kernel<DEG, 8, false, false><<<grid, 128, 0, st>>>(g, r, c, b);
   else if (vec == 4)
-    render_bwd_coop_kernel<DEG, 4, false><<<grid, 128, 0, st>>>(g, r, c, b);
+    render_bwd_coop_kernel<DEG, 4, false, false><<<grid, 128, 0, st>>>(g, r, c, b);
   else
-    render_bwd_coop_kernel<DEG, 0, false><<<grid, 128, 0, st>>>(g, r, c, b);
+    render_bwd_coop_kernel<DEG, 0, false, false><<<grid, 128, 0, st>>>(g, r, c, b);
 }
 
 // The single-pass specular + diffuse render exists in the lane-group forward and the cooperative backward only.
 static bool dual_supported(const GridP& g, const CfgP& c, int vec) {
-  return vec != 0 && !(c.flags & R3D_FLAG_DIFFUSE) &&
-         (unsigned long long)g.W * g.D * g.H * (unsigned long long)(g.stride / 4) <= 0xffffffffull;
+  return vec != 0 && !(c.flags & R3D_FLAG_DIFFUSE) && group_indexable(g);
 }
 template <int DEG>
 static void launch_fwd_dual(dim3 grid, cudaStream_t st, const GridP& g, const RaysP& r, const CfgP& c, const OutP& o) {
@@ -1307,10 +1351,17 @@ static void launch_fwd_dual(dim3 grid, cudaStream_t st, const GridP& g, const Ra
 }
 template <int DEG>
 static void launch_bwd_dual(int vec, dim3 grid, cudaStream_t st, const GridP& g, const RaysP& r, const CfgP& c, const BwdP& b) {
+  if (mask_usable(g, b, vec)) {
+    if (vec == 8)
+      render_bwd_coop_kernel<DEG, 8, true, true><<<grid, 128, 0, st>>>(g, r, c, b);
+    else
+      render_bwd_coop_kernel<DEG, 4, true, true><<<grid, 128, 0, st>>>(g, r, c, b);
+    return;
+  }
   if (vec == 8)
-    render_bwd_coop_kernel<DEG, 8, true><<<grid, 128, 0, st>>>(g, r, c, b);
+    render_bwd_coop_kernel<DEG, 8, true, false><<<grid, 128, 0, st>>>(g, r, c, b);
   else
-    render_bwd_coop_kernel<DEG, 4, true><<<grid, 128, 0, st>>>(g, r, c, b);
+    render_bwd_coop_kernel<DEG, 4, true, false><<<grid, 128, 0, st>>>(g, r, c, b);
 }
 
 // widest vector access the feature layout allows: 8 floats (256-bit loads; records are whole 32-byte sectors),
@@ -1335,6 +1386,12 @@ static int grid_blocks(const RaysP& r, dim3& grid) {
 
 using namespace r3d;
 
+extern "C" int64_t r3d_sample_mask_words(const R3dRays* rays) {
+  RaysP r;
+  if (to_device_params(rays, r)) return -1;
+  return (threads_for_rays(r.n, r.tile_w, r.tile_h) + 127) / 128 * 4;
+}
+
 extern "C" int r3d_render_fwd(const R3dGrid* grid, const R3dRays* rays, const R3dRenderConfig* cfg, const R3dRenderOut* out,
                               void* cuda_stream) {
   GridP g;
@@ -1345,13 +1402,16 @@ extern "C" int r3d_render_fwd(const R3dGrid* grid, const R3dRays* rays, const R3
   if (r.n == 0) return R3D_OK;
   if (!out || !out->colour || !out->depth || !out->acc) return fail(R3D_ERR_INVALID_ARGUMENT, "render output buffers are NULL");
   OutP o{out->colour, out->depth, out->acc, out->disparity, reinterpret_cast<float4*>(out->sample_cache),
-         out->colour_diffuse, reinterpret_cast<float4*>(out->sample_cache_diffuse)};
+         out->colour_diffuse, reinterpret_cast<float4*>(out->sample_cache_diffuse), out->sample_mask};
   if ((o.cache && !aligned16(o.cache)) || (o.cache_diffuse && !aligned16(o.cache_diffuse)))
     return fail(R3D_ERR_INVALID_ARGUMENT, "sample_cache must be 16-byte aligned");
   dim3 blocks;
   if ((rc = grid_blocks(r, blocks))) return rc;
   const int vec = vector_width(g, nullptr);
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  if (o.mask && (!o.cache || !fwd_uses_group_kernel(g, c, vec, o.colour_diffuse ? 0 : cfg->variant, grid->sh_degree)))
+    return fail(R3D_ERR_UNSUPPORTED, "sample_mask needs sample_cache and the default forward kernel (16-byte aligned feature layout with a "
+                                     "stride that is a multiple of 4 floats, no diffuse-only render, variant 0)");
   if (o.colour_diffuse) {  // single-pass specular + diffuse render
     if (!dual_supported(g, c, vec))
       return fail(R3D_ERR_UNSUPPORTED, "colour_diffuse (single-pass specular + diffuse render) needs a 16-byte aligned feature layout "
@@ -1389,7 +1449,8 @@ extern "C" int r3d_render_bwd(const R3dGrid* grid, const R3dRays* rays, const R3
   BwdP b{saved->colour,   saved->depth,        saved->acc,           grad_out->colour,     grad_out->depth,
          grad_out->acc,   grad_out->disparity, grad_grid->densities, grad_grid->features,
          reinterpret_cast<const float4*>(saved->sample_cache),
-         saved->colour_diffuse, grad_out->colour_diffuse, reinterpret_cast<const float4*>(saved->sample_cache_diffuse)};
+         saved->colour_diffuse, grad_out->colour_diffuse, reinterpret_cast<const float4*>(saved->sample_cache_diffuse),
+         saved->sample_mask};
   if ((b.cache && !aligned16(b.cache)) || (b.cache_diffuse && !aligned16(b.cache_diffuse)))
     return fail(R3D_ERR_INVALID_ARGUMENT, "sample_cache must be 16-byte aligned");
   dim3 blocks;

@@ -100,19 +100,23 @@ class _FusedSHVoxGridRender(torch.autograd.Function):
         desc = grid.kernel_desc(densities, features)
         # When a backward pass will follow, the forward keeps (sigmoid(raw) rgb, sigma) of every contributing sample
         # ([S, N, 4] fp32) so that the backward does not gather the 8 corner records a second time.
-        cache = cache_d = None
+        # With the cache goes one ballot word per warp and marching step (which rays' samples contributed): a ReLU-field
+        # backward then marches by those instead of repeating the inside test and the density gather.
+        cache = cache_d = mask = None
         n = origins.shape[0]
         if (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]) and n > 0:
             if _kernels.sample_cache_bytes(n, args.num_samples) * (2 if with_diffuse else 1) <= sample_cache_limit_bytes():
                 cache = _kernels.new_sample_cache(n, args.num_samples, origins.device)
                 cache_d = _kernels.new_sample_cache(n, args.num_samples, origins.device) if with_diffuse else None
-        ctx.desc, ctx.args, ctx.cache, ctx.cache_d, ctx.with_diffuse = desc, args, cache, cache_d, with_diffuse
+                if _kernels.sample_mask_supported(desc, args) and os.environ.get("R3D_SAMPLE_MASK", "1") != "0":
+                    mask = _kernels.new_sample_mask(desc, origins, directions, n, args)
+        ctx.desc, ctx.args, ctx.cache, ctx.cache_d, ctx.mask, ctx.with_diffuse = desc, args, cache, cache_d, mask, with_diffuse
         ctx.set_materialize_grads(False)  # unused outputs arrive as None instead of zero tensors
         if with_diffuse:
-            colour, depth, acc, disparity, colour_d = _kernels.render_forward(desc, origins, directions, args, cache, True, cache_d)
+            colour, depth, acc, disparity, colour_d = _kernels.render_forward(desc, origins, directions, args, cache, True, cache_d, mask)
             ctx.save_for_backward(origins, directions, colour, depth, acc, colour_d)
             return colour, depth, acc, disparity, colour_d
-        colour, depth, acc, disparity = _kernels.render_forward(desc, origins, directions, args, cache)
+        colour, depth, acc, disparity = _kernels.render_forward(desc, origins, directions, args, cache, sample_mask=mask)
         ctx.save_for_backward(origins, directions, colour, depth, acc)
         return colour, depth, acc, disparity
 
@@ -132,8 +136,9 @@ class _FusedSHVoxGridRender(torch.autograd.Function):
             _kernels.render_backward(
                 desc, origins, directions, ctx.args, (colour, depth, acc), (g_colour, g_depth, g_acc, g_disparity), grad_d, grad_f,
                 ctx.cache, diffuse=(colour_d, g_colour_d, ctx.cache_d) if (ctx.with_diffuse and g_colour_d is not None) else None,
+                sample_mask=ctx.mask,
             )
-        ctx.cache = ctx.cache_d = None  # free the per-sample records as soon as they are consumed
+        ctx.cache = ctx.cache_d = ctx.mask = None  # free the per-sample records as soon as they are consumed
         # gradients accumulated into a registered target are already where they belong
         return (None if direct_d is not None else grad_d), (None if direct_f is not None else grad_f), None, None, None, None, None
 
