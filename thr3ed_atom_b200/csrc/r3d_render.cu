@@ -47,6 +47,10 @@
 #ifndef R3D_BWD_BLOCKS
 #define R3D_BWD_BLOCKS 5
 #endif
+// mask-path backward: request the next marching step's per-sample record one step ahead
+#ifndef R3D_BWD_PREFETCH
+#define R3D_BWD_PREFETCH 1
+#endif
 // backward of the single-pass specular + diffuse render: at 5 CTAs/SM (96 registers) it spills 172 bytes; measured
 // 12.52 vs 12.90 ms (c3 step) and 3.07 vs 3.29 ms (32768-ray trainer step) in favour of 4 CTAs/SM (128 registers)
 #ifndef R3D_BWD_DUAL_BLOCKS
@@ -1047,8 +1051,14 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : (DUAL ? R3D_BWD_DUAL_BLOCK
   const unsigned ustride = (unsigned)g.stride;
   const unsigned mask_stride = gridDim.x * 4u, mask_warp = blockIdx.x * 4u + (threadIdx.x >> 5);
   unsigned fmask_next = 0u;
+  float4 cv_next = make_float4(0.f, 0.f, 0.f, 0.f);
   if constexpr (MASK) {
-    if (lo <= hi) fmask_next = __ldg(b.mask + (size_t)lo * mask_stride + mask_warp);
+    if (lo <= hi) {
+      fmask_next = __ldg(b.mask + (size_t)lo * mask_stride + mask_warp);
+#if R3D_BWD_PREFETCH
+      if (alive && ((fmask_next >> lane) & 1u)) cv_next = __ldg(b.cache + (size_t)lo * rp.n + ray);
+#endif
+    }
   }
 
   float T = 1.0f, prefix = 0.f;
@@ -1065,9 +1075,21 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : (DUAL ? R3D_BWD_DUAL_BLOCK
     float draw0[3] = {0.f, 0.f, 0.f};  // DUAL: d L / d raw_diffuse, lands on the k = 0 coefficients only
     unsigned long long key = 0ull;  // 64-bit: voxel offset (up to 2^31) + the low corner's validity pattern
     unsigned fmask = 0u;
+    float4 cv_pre = make_float4(0.f, 0.f, 0.f, 0.f);
     if constexpr (MASK) {
       fmask = fmask_next;
-      if (i < hi) fmask_next = __ldg(b.mask + (size_t)(i + 1) * mask_stride + mask_warp);
+      cv_pre = cv_next;
+      if (i < hi) {
+        fmask_next = __ldg(b.mask + (size_t)(i + 1) * mask_stride + mask_warp);
+#if R3D_BWD_PREFETCH
+        // request the next step's per-sample record now: its HBM latency hides behind this step's sweep
+        if (alive && ((fmask_next >> lane) & 1u)) cv_next = __ldg(b.cache + (size_t)(i + 1) * rp.n + ray);
+#endif
+      }
+      if (fmask == 0u) {  // no ray of this warp contributed at this step: nothing to do, not even the depths
+        have_z = false;   // (the stratum marcher restarts at the next contributing step)
+        continue;
+      }
     }
     if (alive && i >= s.i_lo && i <= s.i_hi) {
       if (!have_z) dm.start(s.dg, i), z = dm.next(s.dg, i), have_z = true;
@@ -1082,7 +1104,11 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : (DUAL ? R3D_BWD_DUAL_BLOCK
         float dpost, sigma;
         float4 cv = make_float4(0.f, 0.f, 0.f, 0.f);
         if constexpr (MASK) {
+#if R3D_BWD_PREFETCH
+          cv = cv_pre;
+#else
           cv = __ldg(b.cache + (size_t)i * rp.n + ray);
+#endif
           sigma = cv.w, dpost = 1.0f;  // ReLU with sigma != 0
         } else {
           sigma = density_post(g.post, density_pre_interp(g, cell), dpost);
