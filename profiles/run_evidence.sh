@@ -11,4 +11,5 @@ tail -2 gpurun_out/${tag}_full.log
 python profiles/ab_kernels.py --variants 0 --density-shift 0.9 > gpurun_out/${tag}_sparse.json 2> gpurun_out/${tag}_sparse.err
 tail -2 gpurun_out/${tag}_sparse.err
 python profiles/extra_bench.py c2 train > gpurun_out/${tag}_extra.json 2> gpurun_out/${tag}_extra.err
+python profiles/dual_bench.py > gpurun_out/${tag}_dual.json 2> gpurun_out/${tag}_dual.err
 tail -c 1500 gpurun_out/${tag}_extra.json
