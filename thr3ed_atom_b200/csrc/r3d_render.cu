@@ -179,6 +179,20 @@ __device__ __forceinline__ void gather_radiance(const GridP& g, const Cell& c, c
     }
 }
 
+// shared-memory reads at a precomputed 32-bit shared address (the member sweep of the cooperative backward forms its
+// addresses as base - index * stride: one IMAD per read)
+__device__ __forceinline__ float lds_f32(unsigned a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void lds_v2(unsigned a, float& x, float& y) {
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(x), "=f"(y) : "r"(a) : "memory");
+}
+__device__ __forceinline__ void lds_v4(unsigned a, float& x, float& y, float& z, float& w) {
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x), "=f"(y), "=f"(z), "=f"(w) : "r"(a) : "memory");
+}
+
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
@@ -226,6 +240,11 @@ struct CoopShape {
   static constexpr int PASSES = 8 / CPP;
   static constexpr int PROW = (NV % 2) ? 4 * NV : 4 * NV + 4;         // row stride: odd multiple of 4 floats => conflict-free
   static constexpr int WROW = 12;                                     // 8 used; 12 keeps 128-bit stores conflict-free
+  // Row of the backward's published weights: [0..7] the 8 corner weights ordered so that the PASSES weights one lane needs
+  // are adjacent (one vector read), [8..15] weight * dL/dsigma_pre per corner (the density gradient needs no second
+  // table), 4 floats of padding (stride 20 floats = 5 x 16 bytes, odd: conflict-free 128-bit stores).
+  static constexpr int WROW2 = 20;
+  __host__ __device__ static constexpr int wpos(int k) { return (k % CPP) * PASSES + (k / CPP); }
 };
 
 // =================================================================================================
@@ -993,9 +1012,8 @@ template <int DEG>
 struct alignas(16) CoopSmem {
   using S = CoopShape<DEG>;
   float P[32 * S::PROW + 64];  // +64: lanes whose float4 index is past the record still read in bounds
-  float W[32 * S::WROW];
+  float W[32 * S::WROW2];
   int V[32 * S::WROW];
-  float D[32];
 };
 
 // DUAL: backward of the single-pass specular + diffuse render: the band-0 image adds g_cd . sigmoid(raw_d_i) to q_i and
@@ -1049,6 +1067,10 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : (DUAL ? R3D_BWD_DUAL_BLOCK
   // in a band-0-only (diffuse) render only the float4s holding a k = 0 coefficient (elements 0, K, 2K) carry gradient
   const bool band_ok = !(DEG > 0 && diffuse) || (cj == 0) || (cj == K / 4) || (cj == (2 * K) / 4);
   const unsigned ustride = (unsigned)g.stride;
+  // per-lane bases into the published tables (the member sweep adds m * row stride)
+  const unsigned w_top = (unsigned)__cvta_generic_to_shared(sm.W + 31 * S::WROW2 + S::PASSES * (cq % S::CPP));
+  const unsigned wd_top = (unsigned)__cvta_generic_to_shared(sm.W + 31 * S::WROW2 + 8 + (lane & 7));
+  const unsigned p_top = (unsigned)__cvta_generic_to_shared(sm.P + 31 * S::PROW + 4 * cj);
   const unsigned mask_stride = gridDim.x * 4u, mask_warp = blockIdx.x * 4u + (threadIdx.x >> 5);
   unsigned fmask_next = 0u;
   float4 cv_next = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1195,13 +1217,17 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : (DUAL ? R3D_BWD_DUAL_BLOCK
         }
         *reinterpret_cast<float4*>(Prow + 4 * j) = make_float4(q4[0], q4[1], q4[2], q4[3]);
       }
-      float* Wrow = sm.W + lane * S::WROW;
-      *reinterpret_cast<float4*>(Wrow) = make_float4(wc[0], wc[1], wc[2], wc[3]);
-      *reinterpret_cast<float4*>(Wrow + 4) = make_float4(wc[4], wc[5], wc[6], wc[7]);
+      float wt[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) wt[S::wpos(k)] = wc[k];
+      float* Wrow = sm.W + lane * S::WROW2;
+      *reinterpret_cast<float4*>(Wrow) = make_float4(wt[0], wt[1], wt[2], wt[3]);
+      *reinterpret_cast<float4*>(Wrow + 4) = make_float4(wt[4], wt[5], wt[6], wt[7]);
+      *reinterpret_cast<float4*>(Wrow + 8) = make_float4(wc[0] * dpre, wc[1] * dpre, wc[2] * dpre, wc[3] * dpre);
+      *reinterpret_cast<float4*>(Wrow + 12) = make_float4(wc[4] * dpre, wc[5] * dpre, wc[6] * dpre, wc[7] * dpre);
       int* Vrow = sm.V + lane * S::WROW;
       *reinterpret_cast<int4*>(Vrow) = make_int4(vox[0], vox[1], vox[2], vox[3]);
       *reinterpret_cast<int4*>(Vrow + 4) = make_int4(vox[4], vox[5], vox[6], vox[7]);
-      sm.D[lane] = dpre;
     }
     // ------------------------------------------------------------------ 3. group by cell, cooperative reduction
     __syncwarp();  // tables visible to the whole warp
@@ -1222,16 +1248,25 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : (DUAL ? R3D_BWD_DUAL_BLOCK
       float ad = 0.f;
       unsigned mm = members;
       while (mm) {
-        const int m = __ffs(mm) - 1;
-        mm &= mm - 1;
-        const float* Wm = sm.W + m * S::WROW;
-        ad = fmaf(Wm[lane & 7], sm.D[m], ad);
-        const float4 p4 = *reinterpret_cast<const float4*>(sm.P + m * S::PROW + 4 * cj);
+        // members are taken from the top (any order will do): z = leading zeros = 31 - lane, one FLO; every table
+        // address is (per-lane base of row 31) - z * (row bytes), one IMAD each
+        const unsigned zc = (unsigned)__clz(mm);
+        mm &= ~(0x80000000u >> zc);
+        float wm[S::PASSES];
+        if constexpr (S::PASSES == 1) {
+          wm[0] = lds_f32(w_top - zc * (4u * S::WROW2));
+        } else if constexpr (S::PASSES == 2) {
+          lds_v2(w_top - zc * (4u * S::WROW2), wm[0], wm[1]);
+        } else {
+          lds_v4(w_top - zc * (4u * S::WROW2), wm[0], wm[1], wm[2], wm[3]);
+        }
+        ad += lds_f32(wd_top - zc * (4u * S::WROW2));
+        float4 p4;
+        lds_v4(p_top - zc * (4u * S::PROW), p4.x, p4.y, p4.z, p4.w);
 #pragma unroll
         for (int pass = 0; pass < S::PASSES; ++pass) {
-          const float wm = Wm[(pass * S::CPP + cq) & 7];
-          a[pass].x = fmaf(wm, p4.x, a[pass].x), a[pass].y = fmaf(wm, p4.y, a[pass].y);
-          a[pass].z = fmaf(wm, p4.z, a[pass].z), a[pass].w = fmaf(wm, p4.w, a[pass].w);
+          a[pass].x = fmaf(wm[pass], p4.x, a[pass].x), a[pass].y = fmaf(wm[pass], p4.y, a[pass].y);
+          a[pass].z = fmaf(wm[pass], p4.z, a[pass].z), a[pass].w = fmaf(wm[pass], p4.w, a[pass].w);
         }
       }
       const int* VL = sm.V + L * S::WROW;
