@@ -127,7 +127,9 @@ typedef struct R3dRenderOut {
    * rays whose sample contributed (sigma != 0); written by the default (lane-group) forward kernel only -- r3d_render_fwd
    * fails with R3D_ERR_UNSUPPORTED if another kernel would be dispatched.  Backward (`saved`): with a ReLU density
    * post-activation the march then needs neither the inside test nor the 8-corner density gather (sigma comes from
-   * sample_cache), and marching steps in which no ray of a warp contributed are skipped outright. */
+   * sample_cache), and marching steps in which no ray of a warp contributed are skipped outright.  The words are indexed
+   * by the launch's warps: the backward call must describe the rays exactly as the forward call did (same num_rays and
+   * tile hint), as it must anyway for the saved outputs to belong to it. */
   uint32_t* sample_mask;
 } R3dRenderOut;
 
