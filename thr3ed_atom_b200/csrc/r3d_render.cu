@@ -1,11 +1,15 @@
 // r3d_render.cu -- fused forward and backward kernels of the SH-voxel-grid renderer (sm_100a).
 //
 // Kernels in this file
-//   render_fwd_coop_kernel   forward, default: per-ray maths + warp-cooperative gather through shared memory
+//   render_fwd_group_kernel  forward, default: per-ray maths; every contributing sample is handed to a group of lanes that
+//                            gathers its 8 corner records straight from global memory (DUAL: also the band-0 image)
+//   render_fwd_coop_kernel   forward, staged variant (A/B): warp-cooperative gather through shared memory (cp.async / TMA)
 //   render_fwd_kernel        forward, one thread per ray end to end (band-0 "diffuse" renders, unpadded layouts, A/B)
-//   render_bwd_coop_kernel   backward, default: per-ray maths + warp-cooperative, cell-merged scatter
+//   render_bwd_coop_kernel   backward, default: per-ray maths + warp-cooperative, cell-merged scatter; MASK: marches by the
+//                            forward's contribution ballots instead of repeating the density probe; DUAL: specular + diffuse
 //   render_bwd_kernel        backward, one thread per ray end to end (A/B)
 //   mark_touched_kernel      measurement helper (unique voxels referenced by a batch)
+// R3dRenderConfig.variant bits (A/B only): 1 per-ray backward, 2 per-ray forward, 4 TMA-staged forward, 8 cp.async-staged forward.
 //
 // Common structure.  One thread owns one ray and marches it front to back.  Per sample it
 //   1. forms the sample position exactly as the reference does (sample.py:54-67),
@@ -27,9 +31,10 @@
 //   q_i = g_c . sigmoid(raw_i) + g_d z_i + g_a,  Total = g_c . C_fg + g_d depth + g_a acc
 // (SURVEY.md A.6).  Gradients are scattered with 128-bit vector reductions (red.global.add.v4.f32).
 //
-// The cooperative kernels exist because of what the profiles showed: the path is bound by the
-// L1 data pipe -- one wavefront per distinct 128-byte line per request -- not by HBM; they make consecutive lanes
-// cover consecutive bytes of ONE voxel record and merge samples that share an interpolation cell.
+// The cooperative kernels exist because of what the profiles showed: the path is bound inside the
+// SM -- L1 data pipe (one wavefront per distinct 128-byte line per request), issue slots -- not by HBM; they make
+// consecutive lanes cover consecutive bytes of ONE voxel record, merge samples that share an interpolation cell
+// (backward) and keep all 32 lanes on contributing samples (forward).
 #include "r3d_host.h"
 
 #include <cstdlib>
