@@ -1254,7 +1254,9 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : (DUAL ? R3D_BWD_DUAL_BLOCK
       unsigned mm = members;
       while (mm) {
         // members are taken from the top (any order will do): z = leading zeros = 31 - lane, one FLO; every table
-        // address is (per-lane base of row 31) - z * (row bytes), one IMAD each
+        // address is (per-lane base of row 31) - z * (row bytes), one IMAD each.  The mask is warp-uniform, so the bit
+        // scan runs on the uniform datapath beside the vector pipes; the classic ffs / mm &= mm - 1 form has 4 fewer
+        // instructions per member but keeps them on the vector ALU and measured slower (4.49 vs 4.36 ms at c3).
         const unsigned zc = (unsigned)__clz(mm);
         mm &= ~(0x80000000u >> zc);
         float wm[S::PASSES];
