@@ -234,6 +234,26 @@ def test_single_pass_specular_and_diffuse_render_host_contract():
         vol_mod.render_rays_with_diffuse(rays, num_samples_per_ray=4)
 
 
+def test_contribution_ballots_are_requested_only_where_the_library_writes_and_uses_them():
+    """``_kernels.sample_mask_supported`` mirrors the dispatch in csrc/r3d_render.cu: the per-step ballots exist only for the
+    default forward kernel (padded layout, all SH bands, variant 0) and only help a ReLU-field backward."""
+    from thr3ed_atom_b200 import _kernels
+
+    cfg = SHVoxGridRenderConfig(8, CameraBounds(1.0, 2.0))
+    relu = _grid(2).kernel_desc()
+    assert _kernels.sample_mask_supported(relu, make_render_args(cfg))
+    assert not _kernels.sample_mask_supported(relu, make_render_args(dataclasses.replace(cfg, render_diffuse=True)))
+    with render_hints(variant=8):
+        assert not _kernels.sample_mask_supported(relu, make_render_args(cfg))
+    softplus = VoxelGrid(
+        densities=torch.rand(4, 5, 6, 1), features=torch.rand(4, 5, 6, 27), voxel_size=VoxelSize(0.5, 0.4, 0.3),
+        density_preactivation=torch.nn.Identity(), density_postactivation=torch.nn.Softplus(), tunable=True,
+    ).kernel_desc()
+    assert not _kernels.sample_mask_supported(softplus, make_render_args(cfg))
+    unpadded = dataclasses.replace(relu, features=torch.rand(4, 5, 6, 27))
+    assert not _kernels.sample_mask_supported(unpadded, make_render_args(cfg))
+
+
 # ---------------------------------------------------------------------------- ray / output glue, cameras
 def test_ray_and_output_containers():
     rays = Rays(torch.arange(24.0).reshape(2, 4, 3), torch.ones(2, 4, 3))
