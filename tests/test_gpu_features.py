@@ -546,7 +546,8 @@ def test_many_samples_per_ray_and_non_contiguous_ray_views(cuda_device):
 # ---------------------------------------------------------------------------------------------
 # backward marching by the forward's contribution ballots (R3dRenderOut.sample_mask)
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("name", ["deg2_16cube", "deg2_jitter", "deg2_sparse", "c1_32cube_deg0", "deg2_random_rays", "deg3_abs", "deg1_aniso_softplus"])
+@pytest.mark.parametrize("name", ["deg2_16cube", "deg2_jitter", "deg2_sparse", "c1_32cube_deg0", "deg2_random_rays", "deg3_abs", "deg1_aniso_softplus",
+                                  "deg3_abs+relu", "deg1_aniso_softplus+relu"])
 def test_backward_by_contribution_ballots_equals_the_density_march(name, cuda_device, monkeypatch):
     """With a ReLU field the backward takes sigma from the forward's per-sample records and the set of contributing samples
     from its per-step ballots instead of repeating the inside test and the density gather: same samples, same sigma bits =>
@@ -555,7 +556,8 @@ def test_backward_by_contribution_ballots_equals_the_density_march(name, cuda_de
     from thr3ed_atom_b200 import _kernels
     from thr3ed_atom_b200.thre3d_reprs.renderers import make_render_args
 
-    case = CASES[name]
+    # "+relu": the degree-1 / degree-3 cases with a ReLU post-activation, so that those instantiations take the ballot march too
+    case = dataclasses.replace(CASES[name[:-5]], density_post="relu") if name.endswith("+relu") else CASES[name]
     inp = build_inputs(case)
     res = {}
     for label, env in (("mask", "1"), ("march", "0")):
