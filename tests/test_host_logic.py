@@ -383,3 +383,21 @@ def test_reference_import_paths_resolve_through_the_compat_shim(monkeypatch):
     assert f is render_sh_voxel_grid and C is SHVoxGridRenderConfig and VG is VoxelGrid and VM is VolumetricModel
     assert R is Rays and CB is CameraBounds
     assert importlib.import_module("thre3d_atom.thre3d_reprs.constants").u_FEATURES == "_features"
+
+
+def test_bench_reports_the_dominant_kernel_in_the_roofline_entry():
+    """bench.py: ``roofline`` is the entry of the render kernel with the longer mean launch; both kernels keep their own keys."""
+    import importlib.util
+    from pathlib import Path
+
+    spec = importlib.util.spec_from_file_location("r3d_bench", Path(__file__).resolve().parent.parent / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    r = bench.roofline_entries(1_500_000_000, 4.5, 4_500_000_000, 4.4, 6500.0, "measured", 3, 5)
+    assert r["roofline"]["kernel"] == "render_fwd_group_kernel" and r["roofline"] == r["roofline_fwd"]
+    assert r["roofline_bwd"]["traffic"] == 5 and r["roofline_fwd"]["traffic"] == 3
+    assert abs(r["roofline_bwd"]["achieved"] - 4.5e9 / 4.4e-3 / 1e9) < 1e-6 and abs(r["roofline_bwd"]["frac"] - r["roofline_bwd"]["achieved"] / 6500.0) < 1e-12
+    r = bench.roofline_entries(1_500_000_000, 4.0, 4_500_000_000, 4.4, 6500.0, "measured")
+    assert r["roofline"]["kernel"] == "render_bwd_coop_kernel" and r["roofline"]["traffic"] is None
+    for key in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert key in r["roofline"]
