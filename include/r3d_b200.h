@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define R3D_ABI_VERSION 4
+#define R3D_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define R3D_API __attribute__((visibility("default")))
@@ -75,6 +75,10 @@ typedef struct R3dGrid {
   float density_scale;     /* expected_density_scale (voxels.py:63,292-294) */
   int32_t density_pre;     /* R3dDensityPre  */
   int32_t density_post;    /* R3dDensityPost */
+  /* Optional derived buffer (NULL = not used): the density quad volume, r3d_density_quad_floats(dims) floats, 16-byte
+   * aligned, filled from `densities` by r3d_build_density_quads.  The caller owns it and must rebuild it whenever the
+   * densities changed.  With it the forward kernel probes the 8 corner densities of a sample with two 16-byte loads. */
+  const float* density_quads;
 } R3dGrid;
 
 /* Pinhole camera for in-kernel ray generation = cast_rays (rendering/volumetric/utils/misc.py:12-50). */
@@ -179,11 +183,25 @@ R3D_API int r3d_grid_lookup_fwd(const R3dGrid* grid, const float* points, int64_
 R3D_API int r3d_grid_lookup_bwd(const R3dGrid* grid, const float* points, int64_t num_points,
                         const float* grad_out, const R3dGridGrad* grad_grid, void* cuda_stream);
 
+/* Density quad volume (see R3dGrid.density_quads): entry (cx, cy, cz) of a [W+2][D+1][H+1] array of float4 holds the
+ * pre-activated, un-scaled densities (v[x][y][z], v[x][y][z+1], v[x][y+1][z], v[x][y+1][z+1]) of x-plane x = cx-1 of the
+ * interpolation cell with low corner (cx-1, cy-1, cz-1); out-of-range voxels are 0 (grid_sample's zero padding,
+ * voxels.py:296-303).  r3d_build_density_quads fills `quads` (writable alias of grid->density_quads) from grid->densities. */
+R3D_API int64_t r3d_density_quad_floats(const int32_t dims[3]);
+R3D_API int r3d_build_density_quads(const R3dGrid* grid, float* quads, void* cuda_stream);
+
 /* Measurement helper (not on the product path): marks every voxel that the batch's in-volume
  * samples reference as an interpolation corner in `bitmap` ([W*D*H] bytes, caller-zeroed), so the
  * host can count U = unique voxels touched for the algorithmic-bytes figure. */
 R3D_API int r3d_mark_touched_voxels(const R3dGrid* grid, const R3dRays* rays, const R3dRenderConfig* cfg,
                             uint8_t* bitmap, void* cuda_stream);
+
+/* Measurement helper (not on the product path): sample statistics of a batch for the roofline companion figures
+ * (SURVEY.md 8d): counters[0] samples visited by the march, [1] samples strictly inside the AABB (voxels.py:252-274),
+ * [2] in-range trilinear corner references of those (what the reference's two grid_sample calls request,
+ * voxels.py:296-318), [3] contributing samples (sigma != 0).  `counters` = 4 device uint64, caller-zeroed, accumulated. */
+R3D_API int r3d_sample_statistics(const R3dGrid* grid, const R3dRays* rays, const R3dRenderConfig* cfg, uint64_t* counters,
+                                  void* cuda_stream);
 
 /* Fused dense Adam on a grid tensor (next-row f1; replaces torch.optim.Adam at trainers.py:242-245,341).
  * p, g, m, v: [n] fp32.  Standard Adam (no weight decay, no amsgrad): bias corrections are passed in

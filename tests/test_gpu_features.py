@@ -482,11 +482,13 @@ def test_cooperative_and_per_ray_kernels_agree(name, cuda_device, monkeypatch):
     gc = torch.from_numpy(inp["grad_colour"]).to(cuda_device)
     results = {}
     for label, variant, cache_limit in (("group+cache", 0, None), ("per-ray+cache", 3, None), ("group", 0, "0"), ("per-ray", 3, "0"),
-                                        ("staged+cache", 8, None), ("staged", 8, "0"), ("staged, TMA", 4, None)):
+                                        ("staged+cache", 8, None), ("staged", 8, "0"), ("staged, TMA", 4, None),
+                                        ("ws+cache", 32, None), ("ws", 32, "0"), ("ws-sort+cache", 96, None), ("ws, no quads", 32, None)):
         if cache_limit is None:
             monkeypatch.delenv("R3D_SAMPLE_CACHE_MAX_BYTES", raising=False)
         else:
             monkeypatch.setenv("R3D_SAMPLE_CACHE_MAX_BYTES", cache_limit)
+        monkeypatch.setenv("R3D_DENSITY_QUADS", "0" if "no quads" in label else "1")
         grid = make_cuda_grid(case, inp, cuda_device)
         hints = {"variant": variant}
         if case.jitter:
@@ -497,7 +499,10 @@ def test_cooperative_and_per_ray_kernels_agree(name, cuda_device, monkeypatch):
         results[label] = (out.colour.detach().clone(), out.depth.detach().clone(), grid.densities.grad.clone(), grid.feature_storage.grad.clone())
     ref = results["per-ray"]
     for label, res in results.items():
-        if label.startswith("group"):
+        if label.startswith("ws"):  # warp-specialised forward: the lane-group arithmetic (up to FMA contraction), any publish order
+            assert (res[0] - results["group"][0]).abs().max().item() < 1e-6, label
+            assert (res[0] - results["ws"][0]).abs().max().item() < 1e-6, label  # with / without cache, sorted or not, quads or not
+        if label.startswith("group") or label.startswith("ws"):
             assert (res[0] - ref[0]).abs().max().item() < 2e-6, label
             assert ((res[1] - ref[1]).abs() <= 2e-6 * ref[1].abs().clamp(min=1.0)).all(), label
         else:
@@ -593,3 +598,34 @@ def test_sample_mask_is_refused_when_another_forward_kernel_would_run(cuda_devic
     args.variant = 0
     with pytest.raises(RuntimeError, match="sample_mask needs"):
         _kernels.render_forward(desc, o, d, args, None, sample_mask=mask)
+
+
+def test_no_grad_render_allocates_no_sample_cache(cuda_device, monkeypatch):
+    """A render under torch.no_grad() on a TUNABLE grid (inference, chunked VolumetricModel.render) must not allocate the
+    [S, N, 4] per-sample records or the ballots: no backward pass can follow (ctx.needs_input_grad alone is True there)."""
+    import thr3ed_atom_b200.thre3d_reprs.renderers as renderers
+    from thr3ed_atom_b200.thre3d_reprs.renderers import render_sh_voxel_grid
+
+    case = CASES["deg2_16cube"]
+    inp = build_inputs(case)
+    grid = make_cuda_grid(case, inp, cuda_device)
+    assert grid.densities.requires_grad
+    calls = {"cache": 0, "mask": 0}
+    real_cache, real_mask = renderers._kernels.new_sample_cache, renderers._kernels.new_sample_mask
+
+    def counting_cache(*a, **k):
+        calls["cache"] += 1
+        return real_cache(*a, **k)
+
+    def counting_mask(*a, **k):
+        calls["mask"] += 1
+        return real_mask(*a, **k)
+
+    monkeypatch.setattr(renderers._kernels, "new_sample_cache", counting_cache)
+    monkeypatch.setattr(renderers._kernels, "new_sample_mask", counting_mask)
+    with torch.no_grad():
+        quiet = render_sh_voxel_grid(grid, _rays(inp, cuda_device), make_cuda_config(case))
+    assert calls == {"cache": 0, "mask": 0}
+    loud = render_sh_voxel_grid(grid, _rays(inp, cuda_device), make_cuda_config(case))
+    assert calls["cache"] == 1
+    assert torch.equal(quiet.colour, loud.colour.detach())

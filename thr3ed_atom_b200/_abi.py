@@ -13,7 +13,7 @@ from typing import Optional
 
 # $R3D_LIB_PATH selects another build of the same library (tuning experiments: other -D flags); default = the in-tree build
 LIB_PATH = Path(os.environ.get("R3D_LIB_PATH") or (Path(__file__).resolve().parent / "_lib" / "libr3d_b200.so"))
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 # enums of r3d_b200.h
 PRE_IDENTITY, PRE_ABS = 0, 1
@@ -38,6 +38,7 @@ class R3dGrid(C.Structure):
         ("density_scale", C.c_float),
         ("density_pre", C.c_int32),
         ("density_post", C.c_int32),
+        ("density_quads", C.c_void_p),
     ]
 
 
@@ -103,6 +104,9 @@ SIGNATURES = {
     "r3d_grid_lookup_fwd": (C.c_int, [C.POINTER(R3dGrid), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "r3d_grid_lookup_bwd": (C.c_int, [C.POINTER(R3dGrid), C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(R3dGridGrad), C.c_void_p]),
     "r3d_mark_touched_voxels": (C.c_int, [C.POINTER(R3dGrid), C.POINTER(R3dRays), C.POINTER(R3dRenderConfig), C.c_void_p, C.c_void_p]),
+    "r3d_sample_statistics": (C.c_int, [C.POINTER(R3dGrid), C.POINTER(R3dRays), C.POINTER(R3dRenderConfig), C.c_void_p, C.c_void_p]),
+    "r3d_density_quad_floats": (C.c_int64, [C.POINTER(C.c_int32 * 3)]),
+    "r3d_build_density_quads": (C.c_int, [C.POINTER(R3dGrid), C.c_void_p, C.c_void_p]),
     "r3d_multimem_all_reduce": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "r3d_adam_step": (
         C.c_int,

@@ -49,6 +49,7 @@ class GridDesc:
     density_scale: float
     density_pre: int
     density_post: int
+    density_quads: Optional[Tensor] = None  # derived probe volume (R3dGrid.density_quads), built by build_density_quads
 
     def to_struct(self) -> _abi.R3dGrid:
         d = _require_cuda(self.densities, "voxel_grid.densities")
@@ -71,6 +72,11 @@ class GridDesc:
         g.norm_bias[:] = [float(b) for b in self.norm_bias]
         g.density_scale = float(self.density_scale)
         g.density_pre, g.density_post = self.density_pre, self.density_post
+        if self.density_quads is not None:
+            q = _require_cuda(self.density_quads, "density_quads")
+            if q.device != d.device or not q.is_contiguous() or q.numel() != density_quad_floats(f.shape[:3]):
+                raise ValueError("density_quads does not belong to this grid")
+            g.density_quads = q.data_ptr()
         return g
 
 
@@ -91,6 +97,7 @@ class RenderArgs:
     image_hw: Optional[Tuple[int, int]] = None  # rays are a row-major H x W image (coherence hint)
     camera: Optional[Tuple[int, int, float, Sequence[float], Sequence[float]]] = None  # (H, W, focal, R9, t3)
     variant: int = 0
+    keep_for_backward: bool = True  # False: no backward pass can follow (torch.no_grad()) -> no sample cache / ballots
 
     def flags(self) -> int:
         return (
@@ -142,6 +149,38 @@ def _pack_call(grid: GridDesc, origins: Optional[Tensor], directions: Optional[T
     return g, r, c, keep
 
 
+def density_quad_floats(dims) -> int:
+    arr = (C.c_int32 * 3)(*[int(x) for x in dims])
+    n = int(_abi.lib().r3d_density_quad_floats(C.byref(arr)))
+    if n < 0:
+        raise ValueError(f"bad grid dims {tuple(dims)}")
+    return n
+
+
+def build_density_quads(grid: GridDesc, quads: Optional[Tensor] = None) -> Tensor:
+    """(Re)build the density quad volume of ``grid`` (see ``R3dGrid.density_quads``) and return it."""
+    device = grid.features.device
+    if quads is None:
+        quads = torch.empty((density_quad_floats(grid.features.shape[:3]),), dtype=torch.float32, device=device)
+    g = dataclasses.replace(grid, density_quads=None).to_struct()
+    with torch.cuda.device(device):
+        _abi.check(_abi.lib().r3d_build_density_quads(C.byref(g), quads.data_ptr(), _stream(device)), "r3d_build_density_quads")
+    return quads
+
+
+def sample_statistics(grid: GridDesc, origins: Optional[Tensor], directions: Optional[Tensor], args: RenderArgs) -> dict:
+    """Measurement helper: samples visited / inside the AABB / in-range corner references / contributing samples."""
+    device = grid.features.device
+    n = origins.shape[0] if args.camera is None else int(args.camera[0]) * int(args.camera[1])
+    counters = torch.zeros((4,), dtype=torch.int64, device=device)
+    g, r, c, keep = _pack_call(grid, origins, directions, n, args)
+    with torch.cuda.device(device):
+        _abi.check(_abi.lib().r3d_sample_statistics(C.byref(g), C.byref(r), C.byref(c), counters.data_ptr(), _stream(device)), "r3d_sample_statistics")
+    del keep
+    v, i, k, s = [int(x) for x in counters.tolist()]
+    return {"samples_visited": v, "samples_inside": i, "corner_refs": k, "samples_contributing": s}
+
+
 def sample_cache_bytes(num_rays: int, num_samples: int) -> int:
     return 16 * num_rays * num_samples
 
@@ -156,7 +195,7 @@ def sample_mask_supported(grid: GridDesc, args: RenderArgs) -> bool:
     the backward use them (ReLU density post-activation)?  Mirrors ``fwd_uses_group_kernel`` / ``mask_usable`` in
     ``csrc/r3d_render.cu``; the library refuses a mask it would not write."""
     f = grid.features
-    return (args.variant == 0 and not args.diffuse and grid.density_post == _abi.POST_RELU and f.shape[3] % 4 == 0
+    return ((args.variant & ~96) == 0 and not args.diffuse and grid.density_post == _abi.POST_RELU and f.shape[3] % 4 == 0
             and f.data_ptr() % 16 == 0 and f.shape[0] * f.shape[1] * f.shape[2] * (f.shape[3] // 4) <= 0xFFFFFFFF)
 
 

@@ -46,6 +46,8 @@ int to_device_params(const R3dGrid* grid, GridP& g) {
     return fail(R3D_ERR_UNSUPPORTED, "unknown density post-activation %d", grid->density_post);
   g.dens = grid->densities;
   g.feat = grid->features;
+  g.quads = reinterpret_cast<const float4*>(grid->density_quads);
+  if (g.quads && !aligned16(g.quads)) return fail(R3D_ERR_INVALID_ARGUMENT, "grid.density_quads must be 16-byte aligned");
   g.W = grid->dims[0], g.D = grid->dims[1], g.H = grid->dims[2];
   g.F = grid->num_features, g.stride = grid->feature_stride, g.K = K;
   for (int a = 0; a < 3; ++a) {

@@ -130,6 +130,40 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
 
 using namespace r3d;
 
+// ---- density quad volume (r3d_device.cuh: CellQ / density_pre_interp_q) ----
+__global__ void __launch_bounds__(256) quads_build_kernel(const float* __restrict__ dens, float4* __restrict__ quads, int W, int D, int H,
+                                                          int pre, unsigned total) {
+  const unsigned idx = blockIdx.x * 256u + threadIdx.x;
+  if (idx >= total) return;
+  const unsigned HZ = (unsigned)H + 1u, DY = (unsigned)D + 1u;
+  const int cz = (int)(idx % HZ), cy = (int)((idx / HZ) % DY), cx = (int)(idx / (HZ * DY));
+  const int x = cx - 1, y = cy - 1, z = cz - 1;
+  auto val = [&](int xx, int yy, int zz) -> float {
+    if ((unsigned)xx >= (unsigned)W || (unsigned)yy >= (unsigned)D || (unsigned)zz >= (unsigned)H) return 0.0f;
+    const float v = __ldg(dens + ((size_t)xx * D + yy) * H + zz);
+    return pre == R3D_PRE_ABS ? fabsf(v) : v;
+  };
+  quads[idx] = make_float4(val(x, y, z), val(x, y, z + 1), val(x, y + 1, z), val(x, y + 1, z + 1));
+}
+
+extern "C" int64_t r3d_density_quad_floats(const int32_t dims[3]) {
+  if (!dims || dims[0] < 1 || dims[1] < 1 || dims[2] < 1) return -1;
+  return 4ll * ((int64_t)dims[0] + 2) * ((int64_t)dims[1] + 1) * ((int64_t)dims[2] + 1);
+}
+
+extern "C" int r3d_build_density_quads(const R3dGrid* grid, float* quads, void* cuda_stream) {
+  GridP g;
+  int rc;
+  if ((rc = to_device_params(grid, g))) return rc;
+  if (!quads || !aligned16(quads)) return fail(R3D_ERR_INVALID_ARGUMENT, "r3d_build_density_quads: quads must be a 16-byte aligned buffer");
+  const long long total = ((long long)g.W + 2) * (g.D + 1) * (g.H + 1);
+  if (total > 0xffffffffLL) return fail(R3D_ERR_UNSUPPORTED, "r3d_build_density_quads: grid too large for 32-bit quad indices");
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  quads_build_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(g.dens, reinterpret_cast<float4*>(quads), g.W, g.D, g.H,
+                                                                                    g.pre, (unsigned)total);
+  return check_launch("r3d_build_density_quads");
+}
+
 extern "C" int r3d_cast_rays(const R3dCamera* camera, float* origins, float* directions, void* cuda_stream) {
   if (!camera || !origins || !directions) return fail(R3D_ERR_INVALID_ARGUMENT, "r3d_cast_rays: NULL argument");
   if (camera->height < 1 || camera->width < 1 || !(camera->focal > 0.f))

@@ -28,6 +28,7 @@ constexpr float kInfinity = 1e10f;   // utils/constants.py:8
 struct GridP {
   const float* __restrict__ dens;
   const float* __restrict__ feat;
+  const float4* __restrict__ quads;  // optional density quad volume (see QuadDims), nullptr = probe `dens` directly
   int W, D, H;
   int F, stride, K;  // features per voxel, record stride (floats), SH coeffs per colour channel
   float lo[3], hi[3], ns[3], nb[3];
@@ -308,6 +309,71 @@ __device__ __forceinline__ void make_cell_inside(const GridP& g, float px, float
 __device__ __forceinline__ bool inside_aabb(const GridP& g, float px, float py, float pz) {
   // strict inequalities, voxels.py:252-274
   return (px > g.lo[0]) && (px < g.hi[0]) && (py > g.lo[1]) && (py < g.hi[1]) && (pz > g.lo[2]) && (pz < g.hi[2]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Density quad volume: a derived, zero-padded copy of the (pre-activated, un-scaled) densities laid out for the
+// probe.  Entry (cx, cy, cz), cx in [0, W+2), cy in [0, D+1), cz in [0, H+1), belongs to the interpolation cell with low
+// corner (x, y, z) = (cx-1, cy-1, cz-1) and holds the four values of its x-plane:
+//     ( v[x][y][z], v[x][y][z+1], v[x][y+1][z], v[x][y+1][z+1] ),   out-of-range voxels = 0
+// so a sample's 8 corner densities are TWO 16-byte loads (entries (cx,cy,cz) and (cx+1,cy,cz)) with no clamping and no
+// validity logic: the zero padding of grid_sample (voxels.py:296-303, padding_mode zeros) is physically in the table.
+// 16 B per entry: 273 MB at 256^3; rebuilt from the parameters by quads_build_kernel (r3d_aux.cu) in ~0.06 ms.
+// ---------------------------------------------------------------------------------------------
+struct CellQ {
+  int ix, iy, iz;              // low corner, each in [-1, dim-1]
+  float wx[2], wy[2], wz[2];   // plain trilinear weights (not zeroed for out-of-range corners)
+};
+
+__device__ __forceinline__ void axis_cell_q(float p, float ns, float nb, int dim, int& i0, float (&w)[2]) {
+  const float n = __fadd_rn(__fmul_rn(p, ns), nb);
+  const float gi = ((n + 1.0f) * (float)dim - 1.0f) * 0.5f;
+  const float fl = floorf(gi);
+  w[0] = (fl + 1.0f) - gi;
+  w[1] = gi - fl;
+  // a point that passed inside_aabb has floor(gi) in [-1, dim-1] (see axis_cell_inside); the clamp only keeps the
+  // address in range whatever the caller passed
+  i0 = min(max((int)fl, -1), dim - 1);
+}
+
+__device__ __forceinline__ void make_cell_q(const GridP& g, float px, float py, float pz, CellQ& c) {
+  axis_cell_q(px, g.ns[0], g.nb[0], g.W, c.ix, c.wx);
+  axis_cell_q(py, g.ns[1], g.nb[1], g.D, c.iy, c.wy);
+  axis_cell_q(pz, g.ns[2], g.nb[2], g.H, c.iz, c.wz);
+}
+
+// the clamped offsets / zeroed weights of the same cell (bit-identical to make_cell_inside), needed only by samples
+// that go on to gather feature records
+__device__ __forceinline__ void cell_from_q(const GridP& g, const CellQ& q, Cell& c) {
+  const int dims[3] = {g.W, g.D, g.H}, mul[3] = {g.D * g.H, g.H, 1}, i0[3] = {q.ix, q.iy, q.iz};
+  const float* w[3] = {q.wx, q.wy, q.wz};
+  int* off[3] = {c.ox, c.oy, c.oz};
+  float* wo[3] = {c.wx, c.wy, c.wz};
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    wo[a][0] = (i0[a] >= 0) ? w[a][0] : 0.0f;
+    wo[a][1] = (i0[a] + 1 < dims[a]) ? w[a][1] : 0.0f;
+    off[a][0] = max(i0[a], 0) * mul[a];
+    off[a][1] = min(i0[a] + 1, dims[a] - 1) * mul[a];
+  }
+}
+
+// same value as density_pre_interp (same products, same order of accumulation; an out-of-range corner adds w * 0
+// instead of 0 * v)
+__device__ __forceinline__ float density_pre_interp_q(const GridP& g, const CellQ& c) {
+  const unsigned plane = (unsigned)(g.D + 1) * (unsigned)(g.H + 1);
+  const unsigned qi = (unsigned)(c.ix + 1) * plane + (unsigned)(c.iy + 1) * (unsigned)(g.H + 1) + (unsigned)(c.iz + 1);
+  const float4 a = __ldg(g.quads + qi), b = __ldg(g.quads + (qi + plane));
+  float s = 0.0f;
+  float wxy = c.wx[0] * c.wy[0];
+  s = fmaf(wxy * c.wz[0], a.x, s), s = fmaf(wxy * c.wz[1], a.y, s);
+  wxy = c.wx[0] * c.wy[1];
+  s = fmaf(wxy * c.wz[0], a.z, s), s = fmaf(wxy * c.wz[1], a.w, s);
+  wxy = c.wx[1] * c.wy[0];
+  s = fmaf(wxy * c.wz[0], b.x, s), s = fmaf(wxy * c.wz[1], b.y, s);
+  wxy = c.wx[1] * c.wy[1];
+  s = fmaf(wxy * c.wz[0], b.z, s), s = fmaf(wxy * c.wz[1], b.w, s);
+  return s * (g.pre == R3D_PRE_ABS ? fabsf(g.dscale) : g.dscale);
 }
 
 // interpolated, pre-activated, scaled density (voxels.py:292-308) -- before the post-activation.

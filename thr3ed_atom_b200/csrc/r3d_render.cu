@@ -846,6 +846,10 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_FWD_BLOCKS) render_fwd
   }
 }
 
+}  // namespace r3d
+#include "r3d_fwd_ws.cuh"
+namespace r3d {
+
 // Per-ray upstream gradients folded into the three numbers the march needs: g_c (3), g_d, g_a, plus
 // Total = sum_i w_i q_i rebuilt from the forward outputs.  Returns false when the ray receives no gradient.
 struct RayGrad {
@@ -1334,6 +1338,49 @@ __global__ void __launch_bounds__(128) mark_touched_kernel(const GridP g, const 
 }
 
 // =================================================================================================
+// measurement helper: sample statistics of a batch (SURVEY.md 8d companion figures)
+//   counters[0] samples visited (conservative in-range march)   counters[1] samples strictly inside the AABB
+//   counters[2] in-range trilinear corner references of those    counters[3] contributing samples (sigma != 0)
+// =================================================================================================
+__global__ void __launch_bounds__(128) sample_stats_kernel(const GridP g, const RaysP rp, const CfgP c, unsigned long long* __restrict__ counters) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long ray = thread_to_ray(rp, t);
+  unsigned visited = 0u, inside = 0u, refs = 0u, contrib = 0u;
+  if (ray >= 0) {
+    RayCtx s;
+    float vx, vy, vz;
+    setup_ray(g, rp, c, ray, s, vx, vy, vz);
+    const Ray& r = s.r;
+    for (int i = s.i_lo; i <= s.i_hi; ++i) {
+      const float z = s.dg.at(i);
+      const float px = __fadd_rn(r.ox, __fmul_rn(r.dx, z));
+      const float py = __fadd_rn(r.oy, __fmul_rn(r.dy, z));
+      const float pz = __fadd_rn(r.oz, __fmul_rn(r.dz, z));
+      ++visited;
+      if (!inside_aabb(g, px, py, pz)) continue;
+      ++inside;
+      Cell cell;
+      make_cell_inside(g, px, py, pz, cell);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int ix = k >> 2, iy = (k >> 1) & 1, iz = k & 1;
+        if (cell.wx[ix] * cell.wy[iy] * cell.wz[iz] != 0.0f) ++refs;
+      }
+      float dpost;
+      if (density_post(g.post, density_pre_interp(g, cell), dpost) != 0.0f) ++contrib;
+    }
+  }
+  unsigned v[4] = {visited, inside, refs, contrib};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    unsigned x = v[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if ((threadIdx.x & 31) == 0 && x) atomicAdd(counters + q, (unsigned long long)x);
+  }
+}
+
+// =================================================================================================
 // host-side dispatch
 // =================================================================================================
 // the lane-group forward addresses records with 32-bit float4 indices
@@ -1349,6 +1396,20 @@ static bool fwd_uses_group_kernel(const GridP& g, const CfgP& c, int vec, int va
 // density post-activation is ReLU (see render_bwd_coop_kernel)
 static bool mask_usable(const GridP& g, const BwdP& b, int vec) {
   return b.mask != nullptr && b.cache != nullptr && vec != 0 && g.post == R3D_POST_RELU;
+}
+
+// warp-specialised forward (r3d_fwd_ws.cuh): 4 producer + 4 consumer warps per CTA, dynamic shared memory
+template <int DEG, bool DUAL, bool SORT>
+static void launch_fwd_ws(dim3 grid, cudaStream_t st, const GridP& g, const RaysP& r, const CfgP& c, const OutP& o) {
+  // the per-CTA stratum table needs one (near, far) for all rays and has to fit beside the stage rings
+  const bool table = r.bounds == nullptr && !(c.flags & R3D_FLAG_OPTIMIZED_SAMPLING) && c.S <= 4096;
+  const size_t smem = ws_smem_bytes<DEG, DUAL>(c.S, table);
+  static const bool attr = [] {
+    cudaFuncSetAttribute(render_fwd_ws_kernel<DEG, DUAL, SORT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws_smem_bytes<DEG, DUAL>(4096, true));
+    return true;
+  }();
+  (void)attr;
+  render_fwd_ws_kernel<DEG, DUAL, SORT><<<grid, 256, smem, st>>>(g, r, c, o, table ? 1 : 0);
 }
 
 template <int DEG>
@@ -1372,7 +1433,12 @@ static void launch_fwd(int vec, int variant, dim3 grid, cudaStream_t st, const G
         return v;
       }();
       (void)carve;
-      render_fwd_group_kernel<DEG, false><<<grid, 128, 0, st>>>(g, r, c, o);
+      if ((variant & 96) == 96)
+        launch_fwd_ws<DEG, false, true>(grid, st, g, r, c, o);
+      else if (variant & 32)
+        launch_fwd_ws<DEG, false, false>(grid, st, g, r, c, o);
+      else
+        render_fwd_group_kernel<DEG, false><<<grid, 128, 0, st>>>(g, r, c, o);
     }
     return;
   }
@@ -1561,4 +1627,19 @@ extern "C" int r3d_mark_touched_voxels(const R3dGrid* grid, const R3dRays* rays,
   if ((rc = grid_blocks(r, blocks))) return rc;
   mark_touched_kernel<<<blocks, 128, 0, static_cast<cudaStream_t>(cuda_stream)>>>(g, r, c, bitmap);
   return check_launch("r3d_mark_touched_voxels");
+}
+
+extern "C" int r3d_sample_statistics(const R3dGrid* grid, const R3dRays* rays, const R3dRenderConfig* cfg, uint64_t* counters,
+                                     void* cuda_stream) {
+  GridP g;
+  RaysP r;
+  CfgP c;
+  int rc;
+  if ((rc = to_device_params(grid, g)) || (rc = to_device_params(rays, r)) || (rc = to_device_params(cfg, r, c))) return rc;
+  if (!counters) return fail(R3D_ERR_INVALID_ARGUMENT, "counters is NULL");
+  if (r.n == 0) return R3D_OK;
+  dim3 blocks;
+  if ((rc = grid_blocks(r, blocks))) return rc;
+  sample_stats_kernel<<<blocks, 128, 0, static_cast<cudaStream_t>(cuda_stream)>>>(g, r, c, reinterpret_cast<unsigned long long*>(counters));
+  return check_launch("r3d_sample_statistics");
 }

@@ -97,14 +97,16 @@ class _FusedSHVoxGridRender(torch.autograd.Function):
     @staticmethod
     def forward(ctx, densities: Tensor, features: Tensor, origins: Tensor, directions: Tensor, grid: VoxelGrid, args: _kernels.RenderArgs,
                 with_diffuse: bool = False):
-        desc = grid.kernel_desc(densities, features)
+        desc = grid.kernel_desc(densities, features, _probe_volume(grid, densities, args))
         # When a backward pass will follow, the forward keeps (sigmoid(raw) rgb, sigma) of every contributing sample
         # ([S, N, 4] fp32) so that the backward does not gather the 8 corner records a second time.
         # With the cache goes one ballot word per warp and marching step (which rays' samples contributed): a ReLU-field
         # backward then marches by those instead of repeating the inside test and the density gather.
         cache = cache_d = mask = None
         n = origins.shape[0]
-        if (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]) and n > 0:
+        # ctx.needs_input_grad is True for a tunable grid even under torch.no_grad(); the caller records whether autograd is
+        # actually recording (args.keep_for_backward), so that inference / chunked no-grad renders store nothing of size N*S
+        if args.keep_for_backward and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]) and n > 0:
             if _kernels.sample_cache_bytes(n, args.num_samples) * (2 if with_diffuse else 1) <= sample_cache_limit_bytes():
                 cache = _kernels.new_sample_cache(n, args.num_samples, origins.device)
                 cache_d = _kernels.new_sample_cache(n, args.num_samples, origins.device) if with_diffuse else None
@@ -143,6 +145,13 @@ class _FusedSHVoxGridRender(torch.autograd.Function):
         return (None if direct_d is not None else grad_d), (None if direct_f is not None else grad_f), None, None, None, None, None
 
 
+def _probe_volume(grid: VoxelGrid, densities: Optional[Tensor], args: _kernels.RenderArgs) -> Optional[Tensor]:
+    """Density quad volume for the warp-specialised forward kernel (None when another kernel will run)."""
+    if not (args.variant & 32) or args.diffuse:
+        return None
+    return grid.density_quads(densities, fresh=args.keep_for_backward)
+
+
 def sample_cache_limit_bytes() -> int:
     """Upper bound on the per-call sample cache (``16 * rays * samples`` bytes); above it the backward re-gathers.
     Default 48 GiB (a B200 has 180 GB); override with ``R3D_SAMPLE_CACHE_MAX_BYTES`` (0 disables the cache)."""
@@ -177,11 +186,12 @@ def make_render_args(cfg: SHVoxGridRenderConfig, **overrides) -> _kernels.Render
         optimized_sampling=bool(cfg.optimized_sampling),
         jitter=hints.get("jitter"),
         image_hw=hints.get("image_hw"),
-        variant=hints.get("variant") or 0,
+        variant=hints.get("variant") or int(os.environ.get("R3D_VARIANT", "0")),
     )
     if args.perturb and args.jitter is None:
         seed = hints.get("rng_seed")
         args.rng_seed = _draw_seed() if seed is None else int(seed)
+    args.keep_for_backward = torch.is_grad_enabled()
     for k, v in overrides.items():
         setattr(args, k, v)
     return args
@@ -261,5 +271,6 @@ def render_sh_voxel_grid_camera(voxel_grid: VoxelGrid, camera_intrinsics, camera
     trans = torch.as_tensor(camera_pose.translation).detach().to("cpu", torch.float32).reshape(3).tolist()
     args = make_render_args(render_config, camera=(int(height), int(width), float(focal), rot, trans), image_hw=None)
     with torch.no_grad():
-        colour, depth, acc, disparity = _kernels.render_forward(voxel_grid.kernel_desc(), None, None, args)
+        desc = voxel_grid.kernel_desc(density_quads=_probe_volume(voxel_grid, None, dataclasses.replace(args, keep_for_backward=False)))
+        colour, depth, acc, disparity = _kernels.render_forward(desc, None, None, args)
     return RenderOut(colour=colour, depth=depth, extra={EXTRA_DISPARITY: disparity, EXTRA_ACCUMULATED_WEIGHTS: acc})

@@ -293,7 +293,29 @@ class VoxelGrid(Module):
         return inside
 
     # ------------------------------------------------------------------ kernels
-    def kernel_desc(self, densities: Optional[Tensor] = None, features: Optional[Tensor] = None) -> _kernels.GridDesc:
+    def density_quads(self, densities: Optional[Tensor] = None, fresh: bool = True) -> Optional[Tensor]:
+        """The density quad volume of the fused forward kernel (``R3dGrid.density_quads``): a derived, zero-padded copy of the
+        pre-activated densities in which a sample's 8 corner values are two 16-byte loads.  It is rebuilt (one ~0.06 ms
+        kernel at 256^3) when ``fresh`` is set -- every differentiable render, i.e. once per training step, because the
+        optimizer has moved the parameters in between -- and otherwise only when the density storage or its version counter
+        changed (chunked no-grad renders of one frame share it).  ``R3D_DENSITY_QUADS=0`` disables it."""
+        import os
+
+        if os.environ.get("R3D_DENSITY_QUADS", "1") == "0":
+            return None
+        d = (self._densities if densities is None else densities).detach()
+        if not d.is_cuda:
+            return None
+        key = (d.data_ptr(), d._version, tuple(d.shape), d.device)
+        buf = self.__dict__.get("_quads_buf")
+        if buf is not None and (buf.device != d.device or buf.numel() != _kernels.density_quad_floats(d.shape[:3])):
+            buf = None
+        if fresh or buf is None or self.__dict__.get("_quads_key") != key:
+            buf = _kernels.build_density_quads(self.kernel_desc(d, None), buf)
+            self.__dict__["_quads_buf"], self.__dict__["_quads_key"] = buf, key
+        return buf
+
+    def kernel_desc(self, densities: Optional[Tensor] = None, features: Optional[Tensor] = None, density_quads: Optional[Tensor] = None) -> _kernels.GridDesc:
         """Descriptor handed to the C ABI (pointers + the fp32 constants of the point -> grid map)."""
         if not (_is_identity(self._feature_preactivation) and _is_identity(self._feature_postactivation)):
             raise NotImplementedError("feature pre-/post-activations other than Identity are not supported by the fused B200 kernels")
@@ -309,6 +331,7 @@ class VoxelGrid(Module):
             density_scale=float(self._expected_density_scale),
             density_pre=pre_id,
             density_post=post_id,
+            density_quads=density_quads,
         )
 
     def forward(self, points: Tensor, viewdirs: Optional[Tensor] = None) -> Tensor:
