@@ -8,11 +8,15 @@
 Workload (BASELINE.json configs[2], the configuration the metric is quoted on): a 256^3 SH-degree-2
 ReLU-field voxel grid (U(-1,1) init, 3x3x3 world, expected_density_scale 33.33), one 800x800 "hotdog
 shape" pinhole camera (pose_spherical(30, 60, 4.031128), focal 1111.11, bounds 1.8..6.6), 256 stratified
-(jittered) samples per ray, white background, L1 loss against U(0,1) pixels.  One STEP = one pass of
-the hot path over the whole 640 000-ray batch through the public API:
-    render_rays (fused forward kernel) -> l1_loss -> backward (gradient zero-fill + fused backward kernel)
-At N > 1 every rank renders its own camera view of the same grid (weak scaling: 640 000 rays per GPU)
-and the step ends with the NCCL all-reduce of the grid gradient (the path's only exchange).
+(jittered) samples per ray, white background, L1 loss against U(0,1) pixels.  One STEP = one full training
+step over the whole 640 000-ray batch through the public API, as the reference trainer runs it
+(modules/trainers.py:339-341: zero_grad -> backward -> optimizer.step):
+    zero_grad -> render_rays (fused forward kernel) -> l1_loss -> backward (fused backward kernel) -> Adam step
+At N = 1 the optimizer is the fused dense Adam kernel.  At N > 1 every rank renders its own camera view of the
+same replicated grid (weak scaling: 640 000 rays per GPU) and gradient exchange + optimizer are ONE in-switch
+kernel: reduce-scatter -> shard-local Adam -> all-gather over NVLink/NVSwitch multicast (csrc/r3d_comm.cu);
+`--exchange nccl` = NCCL all-reduce + local Adam.  `--no-optimizer` gives the round-1 step (forward + backward
++ gradient all-reduce); the line also carries that number as `fwd_bwd_only`.
 
 Printed JSON (one line, rank 0): see the keys at the bottom; `value` is device-resident throughput,
 `e2e` is the same step with rays/pixels coming from pinned host memory and the rendered colour +
@@ -138,7 +142,7 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port (reference algorithm, ATen CPU kernels), bounded ray sample
 # ------------------------------------------------------------------------------------------------
-def cpu_oracle_rays_per_sec(workload: str, sample_rays: int, steps: int, warmup: int, threads: int):
+def cpu_oracle_rays_per_sec(workload: str, sample_rays: int, steps: int, warmup: int, threads: int, with_optimizer: bool = True):
     from oracle import torch_port as tp
 
     grid_n, deg, side, spp = WORKLOADS[workload]
@@ -169,7 +173,20 @@ def cpu_oracle_rays_per_sec(workload: str, sample_rays: int, steps: int, warmup:
         if it >= warmup:
             times.append(dt)
     mean = float(np.mean(times))
-    return idx.numel() / mean, mean, idx.numel()
+    if not with_optimizer:
+        return idx.numel() / mean, mean, idx.numel(), 0.0
+    # the step's optimizer half: torch.optim.Adam over the dense grid, as the reference trainer builds it
+    # (modules/trainers.py:242-245); its cost does not depend on the ray count, so it is timed once on the full grid
+    pd, pf = dens.clone().requires_grad_(True), feat.clone().requires_grad_(True)
+    opt = torch.optim.Adam([{"params": [pd, pf], "lr": 1e-5}], betas=(0.9, 0.999))
+    pd.grad, pf.grad = torch.zeros_like(pd), torch.zeros_like(pf)
+    opt.step()
+    t0 = time.perf_counter()
+    opt.step()
+    adam_s = time.perf_counter() - t0
+    # full-step throughput extrapolated from the sample: the render part scales with the rays, the optimizer part does not
+    full = n * mean / idx.numel() + adam_s
+    return n / full, mean, idx.numel(), adam_s
 
 
 def run_reference_arm(args):
@@ -181,8 +198,11 @@ def run_reference_arm(args):
     workload = args.workload
     threads = os.cpu_count() or 1
     steps, warmup = args.steps, max(1, min(args.warmup, 2))
-    rps, mean_s, sample = cpu_oracle_rays_per_sec(workload, args.cpu_sample_rays, steps, warmup, threads)
+    rps, mean_s, sample, adam_s = cpu_oracle_rays_per_sec(workload, args.cpu_sample_rays, steps, warmup, threads,
+                                                          with_optimizer=not getattr(args, "no_optimizer", False))
     grid_n, deg, side, spp = WORKLOADS[workload]
+    n_full = side * side
+    mean_s = n_full / rps  # extrapolated full-batch step
     line = {
         "impl": "reference",
         "metric": METRIC, "value": rps, "unit": "rays/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
@@ -191,25 +211,100 @@ def run_reference_arm(args):
         "config": {"workload": workload, "grid": grid_n, "sh_degree": deg, "image": [side, side], "samples_per_ray": spp,
                    "rays_per_step": sample, "device": "cpu"},
         "cpu_baseline": {"value": rps, "unit": "rays/s", "cores": threads, "kind": "port",
-                         "sample": f"{sample} strided rays of the {side}x{side} view per step, fwd+bwd, chunked like the reference must be"},
+                         "sample": f"{sample} strided rays of the {side}x{side} view per step (fwd+bwd, chunked like the reference must be), "
+                                   f"extrapolated to the {n_full}-ray batch, + one dense torch.optim.Adam step over the grid ({adam_s:.2f} s)"},
         "e2e": {"value": rps, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def roofline_entries(bytes_fwd, fwd_ms, bytes_bwd, bwd_ms, peak, peak_src, traffic_fwd=None, traffic_bwd=None):
+def fp32_peak_tflops(sm_mhz: float, sms: int = 148) -> float:
+    """FP32 SIMT peak: SMs x 128 lanes x 2 flop x clock (SURVEY.md 8d companion figure)."""
+    return sms * 128 * 2 * sm_mhz * 1e6 / 1e12
+
+
+def roofline_entries(bytes_fwd, fwd_ms, bytes_bwd, bwd_ms, peak, peak_src, traffic, stats, rec_bytes, nf, sm_mhz):
     """HBM-roofline entries of the two render kernels: ALGORITHMIC bytes / mean launch duration / measured
     peak.  ``roofline`` is the entry of the DOMINANT kernel (the one with the longer mean launch); both kernels are also
-    reported under their own keys."""
-    def entry(kernel, nbytes, ms, traffic):
-        achieved = nbytes / (ms * 1e-3) / 1e9
-        return {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes": nbytes, "kernel_ms": ms}
+    reported under their own keys, each with the 8d companion figures: gather-request bytes (what the reference's two
+    grid_sample calls request: in-range corner references x record bytes) and the FP32 work against the SIMT peak."""
+    # FMA counts per sample: probe = 8-corner density interpolation + position/cell arithmetic; a contributing sample adds
+    # the 8 x F record contraction, the SH weighting and compositing (forward), and the same contraction transposed plus
+    # the chain rule (backward)
+    fma_probe, fma_fwd, fma_bwd = 8 + 30, 8 * nf + nf + 24, 8 * nf + nf + 8 + 40
+    flops_fwd = 2.0 * (stats["samples_inside"] * fma_probe + stats["samples_contributing"] * fma_fwd)
+    flops_bwd = 2.0 * stats["samples_contributing"] * (fma_bwd + 20)
+    fp32_peak = fp32_peak_tflops(sm_mhz)
 
-    fwd = entry("render_fwd_group_kernel", bytes_fwd, fwd_ms, traffic_fwd)
-    bwd = entry("render_bwd_coop_kernel", bytes_bwd, bwd_ms, traffic_bwd)
+    def entry(kernel, nbytes, ms, key, flops, requests):
+        achieved = nbytes / (ms * 1e-3) / 1e9
+        tf = flops / (ms * 1e-3) / 1e12
+        return {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic.get(key), "traffic_source": traffic.get("source"), "peak_source": peak_src,
+                "algorithmic_bytes": nbytes, "kernel_ms": ms,
+                "gather_request_bytes": requests, "fp32_flops": flops, "fp32_tflops": tf, "fp32_peak_tflops": fp32_peak,
+                "fp32_frac": tf / fp32_peak}
+
+    requests = stats["corner_refs"] * rec_bytes
+    fwd = entry("render_fwd_group_kernel", bytes_fwd, fwd_ms, "render_fwd_dram_bytes", flops_fwd, requests)
+    bwd = entry("render_bwd_coop_kernel", bytes_bwd, bwd_ms, "render_bwd_dram_bytes", flops_bwd, requests)
     return {"roofline": dict(fwd if fwd_ms > bwd_ms else bwd), "roofline_fwd": fwd, "roofline_bwd": bwd}
+
+
+def load_traffic(workload: str) -> dict:
+    """ncu-measured DRAM bytes per launch (profiles/traffic.json, written by profiles/measure_traffic.py on the GPU box).
+    The file is stamped with the digest of the library sources it was measured with; a stale file yields null, not a
+    number that no longer describes the kernels."""
+    path = ROOT / "profiles" / "traffic.json"
+    try:
+        from thr3ed_atom_b200 import build as _build
+
+        data = json.loads(path.read_text())
+        if data.get("lib_digest") != _build._source_digest():
+            return {"source": "profiles/traffic.json is stale (library sources changed since it was measured): re-run profiles/measure_traffic.py"}
+        entry = dict(data.get(workload, {}))
+        entry["source"] = f"ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, {data.get('measured', '?')}"
+        return entry
+    except Exception as e:  # noqa: BLE001
+        return {"source": f"unavailable ({e.__class__.__name__})"}
+
+
+def pytorch_gpu_baseline(workload: str, device, chunk: int = 32768, chunks: int = 4):
+    """Informational row: the reference's op-by-op PyTorch path (the oracle port: same ATen ops in the
+    same order) on the SAME B200, forward + backward, ray-chunked at 32768 as the reference itself has to be
+    (modules/volumetric_model.py:151-167), on a bounded sample of the view's rows."""
+    import dataclasses
+
+    from oracle import torch_port as tp
+
+    grid_n, deg, side, spp = WORKLOADS[workload]
+    dens, feat = make_grid_values(grid_n, deg)
+    grid = tp.OracleGrid(dens.to(device), feat.to(device), tuple(w / grid_n for w in WORLD), (0.0, 0.0, 0.0), density_scale(), "identity", "relu")
+    rot, trans, focal = camera_for_rank(0, side)
+    origins, dirs = tp.cast_pinhole_rays(side, side, focal, rot, trans)
+    n = origins.shape[0]
+    gen = torch.Generator().manual_seed(7)
+    pixels = torch.rand((n, 3), generator=gen)
+    times = []
+    for it in range(chunks + 1):
+        start = ((it * 7919 * chunk) % max(1, n - chunk)) // side * side  # whole rows, spread over the image
+        o, d, px = (t[start:start + chunk].to(device) for t in (origins, dirs, pixels))
+        jitter = torch.rand((o.shape[0], spp), device=device)
+        dq, fq = grid.densities.detach().requires_grad_(True), grid.features.detach().requires_grad_(True)
+        torch.cuda.synchronize(device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = tp.render(dataclasses.replace(grid, densities=dq, features=fq), o, d, num_samples=spp, near=NEAR, far=FAR, jitter=jitter, white_bkgd=True)
+        torch.nn.functional.l1_loss(out["colour"], px).backward()
+        e1.record()
+        torch.cuda.synchronize(device)
+        if it > 0:
+            times.append(e0.elapsed_time(e1))
+        del out, dq, fq
+    ms = float(np.mean(times))
+    return {"value": chunk / (ms * 1e-3), "unit": "rays/s", "kind": "port (oracle/torch_port.py on cuda: the reference's ATen op sequence)",
+            "sample": f"{chunks} chunks of {chunk} rays of the same view, fwd+bwd, {ms:.1f} ms per chunk", "ms_per_chunk": ms}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -224,13 +319,19 @@ def main():
     ap.add_argument("--workload", default="c3_256cube_deg2_800px_256spp", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-sample-rays", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the informational PyTorch-on-the-same-GPU row")
     ap.add_argument("--no-perturb", action="store_true")
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--flat-order", action="store_true", help="do not pass the image-shape hint (rays in list order)")
-    ap.add_argument("--reducer", default=os.environ.get("R3D_BENCH_REDUCER", "auto"), choices=["auto", "nccl", "nvls"],
-                    help="N>1: gradient exchange = NCCL all-reduce, or the in-switch multimem kernel (csrc/r3d_comm.cu). "
-                         "auto = nvls at 8+ ranks (measured 4.04 vs 4.18 ms), nccl below (at 2 ranks the multicast path "
-                         "moves 1.5x the ring's bytes: 4.9 vs 3.3 ms)")
+    ap.add_argument("--no-optimizer", action="store_true",
+                    help="round-1 step definition: forward + backward (+ gradient all-reduce at N > 1), no optimizer step")
+    ap.add_argument("--lr", type=float, default=1e-5,
+                    help="Adam rate of the timed steps: the full update is computed and written; the rate is small so that the "
+                         "U(-1,1) statistics of the synthetic grid (hence the workload) do not drift over the run")
+    ap.add_argument("--exchange", default=os.environ.get("R3D_BENCH_EXCHANGE", "auto"), choices=["auto", "fused", "nccl", "nvls"],
+                    help="N>1: fused = in-switch reduce-scatter -> shard-local Adam -> all-gather kernel (csrc/r3d_comm.cu); "
+                         "nccl = NCCL all-reduce then the local fused Adam; nvls = in-switch all-reduce kernel then the local fused "
+                         "Adam; auto = fused when NVLS multicast is available, else nccl")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -241,6 +342,7 @@ def main():
 
     from thr3ed_atom_b200 import _kernels
     from thr3ed_atom_b200.modules.volumetric_model import VolumetricModel
+    from thr3ed_atom_b200.optim import FusedGridAdam
     from thr3ed_atom_b200.rendering.volumetric.render_interface import Rays
     from thr3ed_atom_b200.rendering.volumetric.utils.misc import cast_rays, flatten_rays
     from thr3ed_atom_b200.thre3d_reprs.renderers import SHVoxGridRenderConfig, make_render_args, render_hints, render_sh_voxel_grid
@@ -262,12 +364,13 @@ def main():
 
     grid_n, deg, side, spp = WORKLOADS[args.workload]
     nf = 3 * (deg + 1) ** 2
-    if grid_n**3 * (nf + 1) * 4 > 8 * 2**30:
+    big = grid_n**3 * (nf + 1) * 4 > 8 * 2**30
+    if big:
         # 512^3 deg 3 is 26 GB per replica: draw it on the device (same U(-1,1) law, same seed on every rank)
         gdev = torch.Generator(device=device).manual_seed(42)
         dens = torch.empty((grid_n, grid_n, grid_n, 1), dtype=torch.float32, device=device).uniform_(-1.0, 1.0, generator=gdev)
         feat = torch.empty((grid_n, grid_n, grid_n, nf), dtype=torch.float32, device=device).uniform_(-1.0, 1.0, generator=gdev)
-        args.no_cpu_baseline = True
+        args.no_cpu_baseline = args.no_gpu_baseline = True
     else:
         dens, feat = make_grid_values(grid_n, deg)
     voxel_grid = VoxelGrid(
@@ -290,18 +393,19 @@ def main():
     colour_host = torch.empty((n_rays, 3), dtype=torch.float32).pin_memory()
     hint = None if args.flat_order else (side, side)
 
-    # ---- algorithmic bytes: exact count of touched voxels (untimed bitmap pass) ----
+    # ---- algorithmic bytes + companion figures: exact counts from untimed passes over the same rays ----
     with render_hints(image_hw=hint, rng_seed=1234):
         margs = make_render_args(cfg)
     bitmap = _kernels.mark_touched_voxels(voxel_grid.kernel_desc(), rays.origins, rays.directions, margs)
     touched = int(bitmap.sum().item())
     del bitmap
+    stats = _kernels.sample_statistics(voxel_grid.kernel_desc(), rays.origins, rays.directions, margs)
     rec_bytes = 4 * (nf + 1)  # one (density + SH) voxel record
     bytes_fwd = touched * rec_bytes + 48 * n_rays
     bytes_bwd = 3 * touched * rec_bytes + 60 * n_rays
 
     # kernel-level CUDA events (on the launching stream = torch's current stream)
-    ev = {"fwd": [], "bwd": []}
+    ev = {"fwd": [], "bwd": [], "opt": []}
     real_fwd, real_bwd = _kernels.render_forward, _kernels.render_backward
 
     def timed(name, fn):
@@ -327,52 +431,145 @@ def main():
     _renderers._kernels.render_forward = counted(timed("fwd", real_fwd))
     _renderers._kernels.render_backward = counted(timed("bwd", real_bwd))
 
+    # ---- exchange + optimizer (reference modules/trainers.py:339-341: zero_grad -> backward -> optimizer.step) ----
     params = list(voxel_grid.parameters())
-    reducer = None
-    want_nvls = args.reducer == "nvls" or (args.reducer == "auto" and world >= 8)
-    if world > 1 and want_nvls:
-        from thr3ed_atom_b200.distributed import NVLSGradientReducer
-
-        # gradients live in symmetric memory; the NVSwitch reduces them in place.  Every rank must take the same branch,
-        # so a failure anywhere (no multicast support) sends all ranks to NCCL.
+    betas, eps = (0.9, 0.999), 1e-8
+    reducer = sharded = local_opt = None
+    exchange = "none"
+    if world > 1:
+        want = args.exchange
         ok = torch.ones(1, device=device)
-        try:
-            reducer = NVLSGradientReducer(voxel_grid)
-        except Exception as e:  # noqa: BLE001
-            if args.reducer == "nvls":
-                raise
-            ok.zero_()
-            print(f"[bench] rank {rank}: NVLS reducer unavailable ({e!r}); using NCCL", file=sys.stderr)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        if float(ok.item()) == 0.0 and reducer is not None:
-            reducer.close()
-            for p in voxel_grid.parameters():
-                p.grad = None
-            reducer = None
+        if want in ("auto", "fused") and not args.no_optimizer:
+            from thr3ed_atom_b200.distributed import NVLSShardedAdam
+
+            # every rank must take the same branch, so a failure anywhere (no multicast support) sends all ranks to NCCL
+            try:
+                sharded = NVLSShardedAdam(voxel_grid, lr=args.lr, betas=betas, eps=eps)
+            except Exception as e:  # noqa: BLE001
+                if want == "fused":
+                    raise
+                ok.zero_()
+                print(f"[bench] rank {rank}: fused NVLS optimizer unavailable ({e!r}); using NCCL", file=sys.stderr)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if float(ok.item()) == 0.0:
+                if sharded is not None:
+                    sharded.close()
+                sharded = None
+            exchange = "fused" if sharded is not None else "nccl"
+        elif want == "nvls" or (want in ("auto", "fused") and args.no_optimizer):
+            from thr3ed_atom_b200.distributed import NVLSGradientReducer
+
+            try:
+                reducer = NVLSGradientReducer(voxel_grid)
+            except Exception as e:  # noqa: BLE001
+                if want == "nvls":
+                    raise
+                ok.zero_()
+                print(f"[bench] rank {rank}: NVLS reducer unavailable ({e!r}); using NCCL", file=sys.stderr)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if float(ok.item()) == 0.0 and reducer is not None:
+                reducer.close()
+                for p in params:
+                    p.grad = None
+                reducer = None
+            exchange = "nvls" if reducer is not None else "nccl"
+        else:
+            exchange = "nccl"
+    if not args.no_optimizer and sharded is None:
+        local_opt = FusedGridAdam([{"params": params, "lr": args.lr}], betas=betas, eps=eps)
+
+    def exchange_and_update():
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        if sharded is not None:
+            sharded.step()  # barrier -> reduce-scatter / Adam / all-gather in one kernel -> barrier
+            launches["n"] += 1
+        else:
+            if reducer is not None:
+                reducer.all_reduce()
+                launches["n"] += 1
+            elif world > 1:
+                for p in params:  # the path's only exchange: sum of the per-rank dense grid gradients
+                    dist.all_reduce(p.grad, op=dist.ReduceOp.SUM)
+            if local_opt is not None:
+                local_opt.step()
+                launches["n"] += len(params)
+        e1.record()
+        ev["opt"].append((e0, e1))
 
     def step(o, d, px):
+        if sharded is not None:
+            sharded.zero_grad()  # same 1.95 GB memset as autograd's fresh zero-filled buffers
+        elif reducer is not None:
+            reducer.zero_grad()
+        else:
+            for p in params:
+                p.grad = None  # autograd then hands the backward kernel freshly zero-filled buffers
         with render_hints(image_hw=hint, variant=args.variant):
             out = vol_mod.render_rays(Rays(o, d))
         loss = torch.nn.functional.l1_loss(out.colour, px)
-        if reducer is not None:
-            reducer.zero_grad()  # same 1.95 GB memset as autograd's fresh zero-filled buffers
-            loss.backward()  # the backward kernel accumulates straight into the symmetric buffers
-            reducer.all_reduce()
-            launches["n"] += 1  # r3d multimem all-reduce kernel
-            return loss, out
-        for p in params:
-            p.grad = None
-        loss.backward()
-        if world > 1:
-            # the path's only exchange: sum of the per-rank dense grid gradients
-            for p in params:
-                dist.all_reduce(p.grad, op=dist.ReduceOp.SUM)
+        loss.backward()  # with a direct target the backward kernel accumulates straight into the symmetric buffers
+        exchange_and_update()
         return loss, out
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    # ---- N > 1: one untimed step checks the exchange against an independent NCCL reduction of a strided probe ----
+    parity = None
+    if world > 1:
+        flat_g = sharded.grad_flat if sharded is not None else (reducer.flat if reducer is not None else None)
+        total = sum(p.numel() for p in params)
+        stride = max(1, total // (1 << 20))
+        if sharded is not None:
+            idx = torch.arange(0, sharded.total, stride, device=device)
+            p_before = sharded.param_flat[idx].clone()
+            sharded.zero_grad()
+            with render_hints(image_hw=hint, variant=args.variant):
+                out = vol_mod.render_rays(rays)
+            torch.nn.functional.l1_loss(out.colour, pixels).backward()
+            g_sum = flat_g[idx].clone()
+            dist.all_reduce(g_sum, op=dist.ReduceOp.SUM)  # NCCL on 1 M probe elements: the independent path
+            sharded.step()  # first step: exp_avg = exp_avg_sq = 0  =>  p -= lr * g / (|g| + eps) up to rounding
+            torch.cuda.synchronize()
+            want_p = p_before - args.lr * (g_sum / (g_sum.abs() + eps))
+            got_p = sharded.param_flat[idx]
+            err = float(((got_p - want_p).abs().max() / args.lr).item())
+            spread = got_p.clone()
+            lo_, hi_ = spread.clone(), spread.clone()
+            dist.all_reduce(lo_, op=dist.ReduceOp.MIN), dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
+            replicas_equal = bool(torch.equal(lo_, hi_))
+            moved = float(((got_p - p_before).abs() > 0).float().mean().item())
+            parity = {"what": "fused reduce-scatter/Adam/all-gather vs NCCL all-reduce of a strided probe + closed-form first Adam step",
+                      "probe_elements": int(idx.numel()), "max_err_over_lr": err, "replicas_identical": replicas_equal,
+                      "fraction_of_probe_updated": moved, "ok": bool(err < 1e-3 and replicas_equal and moved > 0.1)}
+        else:
+            for p in params:
+                p.grad = None
+            if reducer is not None:
+                reducer.zero_grad()
+            with render_hints(image_hw=hint, variant=args.variant):
+                out = vol_mod.render_rays(rays)
+            torch.nn.functional.l1_loss(out.colour, pixels).backward()
+            grads = [p.grad.reshape(-1) for p in params]
+            idxs = [torch.arange(0, g.numel(), stride, device=device) for g in grads]
+            local = torch.cat([g[i] for g, i in zip(grads, idxs)]).clone()
+            dist.all_reduce(local, op=dist.ReduceOp.SUM)
+            if reducer is not None:
+                reducer.all_reduce()
+            else:
+                for p in params:
+                    dist.all_reduce(p.grad, op=dist.ReduceOp.SUM)
+            torch.cuda.synchronize()
+            got = torch.cat([p.grad.reshape(-1)[i] for p, i in zip(params, idxs)])
+            err = float(((got - local).abs().max() / local.abs().max().clamp(min=1e-30)).item())
+            parity = {"what": f"{exchange} all-reduce of the grid gradient vs an independent NCCL reduction of a strided probe",
+                      "probe_elements": int(local.numel()), "max_rel_err": err, "ok": bool(err < 1e-4)}
+        worst = torch.tensor([0.0 if parity["ok"] else 1.0], device=device)
+        dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+        parity["ok"] = bool(float(worst.item()) == 0.0)
 
     # ---- warm-up + timed region (device-resident inputs).  The clock sampler runs from the first warm-up step on:
     #      nvidia-smi needs ~100 ms to start, the timed region itself can be shorter than that. ----
@@ -381,7 +578,8 @@ def main():
         for _ in range(args.warmup):
             step(rays.origins, rays.directions, pixels)
         barrier()
-        ev["fwd"].clear(), ev["bwd"].clear()
+        for k in ev:
+            ev[k].clear()
         launches["n"] = 0
         barrier()
         start.record()
@@ -393,6 +591,7 @@ def main():
     gpu_launches = launches["n"]
     fwd_ms = float(np.mean([a.elapsed_time(b) for a, b in ev["fwd"]]))
     bwd_ms = float(np.mean([a.elapsed_time(b) for a, b in ev["bwd"]]))
+    opt_ms = float(np.mean([a.elapsed_time(b) for a, b in ev["opt"]]))
 
     # ---- e2e: host buffers in, loss + colour out, every step.  The step's inputs (rays + pixels, 23 MB) are copied from
     #      pinned host memory on a copy stream while the previous step computes (what a data loader does); every step's
@@ -428,27 +627,33 @@ def main():
     e2e_s = time.perf_counter() - t0
 
     # ---- max over ranks ----
-    t = torch.tensor([total_ms, e2e_s * 1e3, fwd_ms, bwd_ms], dtype=torch.float64, device=device)
+    t = torch.tensor([total_ms, e2e_s * 1e3, fwd_ms, bwd_ms, opt_ms], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, fwd_ms, bwd_ms = [float(x) for x in t.tolist()]
+    total_ms, e2e_ms, fwd_ms, bwd_ms, opt_ms = [float(x) for x in t.tolist()]
+    peak_mem_gb = torch.cuda.max_memory_allocated(device) / 1e9
 
     if rank == 0:
         peaks_path = ROOT / "MEASURED_PEAKS.json"
+        sm_max = 1965.0
         if peaks_path.exists():
-            peak, peak_src = float(json.loads(peaks_path.read_text())["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured)"
+            pk = json.loads(peaks_path.read_text())
+            peak, peak_src = float(pk["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured)"
+            sm_max = float(pk.get("sm_max_mhz", sm_max))
         else:
             peak, peak_src = 6650.0, "B200_PROFILING.md fallback"
-        traffic_fwd = traffic_bwd = None
-        tp_path = ROOT / "profiles" / "traffic.json"
-        if tp_path.exists():
-            try:
-                measured = json.loads(tp_path.read_text()).get(args.workload, {})
-                traffic_fwd, traffic_bwd = measured.get("render_fwd_dram_bytes"), measured.get("render_bwd_dram_bytes")
-            except Exception:
-                traffic_fwd = traffic_bwd = None
+        clock_summary = clocks.summary()
+        sm_mhz = clock_summary.get("sm_mhz") or sm_max
         ms_per_step = total_ms / args.steps
         value = world * n_rays / (ms_per_step * 1e-3)
+        opt_name = ("none" if args.no_optimizer else
+                    ("in-switch reduce-scatter -> shard-local Adam -> all-gather (r3d_multimem_adam_step)" if sharded is not None else
+                     (f"{exchange} all-reduce(grid grad) + " if world > 1 else "") + "fused dense Adam (r3d_adam_step)"))
+        step_desc = "zero_grad + render_rays fwd + l1_loss + backward (fused bwd)"
+        if args.no_optimizer:
+            step_desc += f" + {exchange} all-reduce(grid grad)" if world > 1 else ""
+        else:
+            step_desc += " + optimizer.step: " + opt_name
         line = {
             "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -456,25 +661,42 @@ def main():
             "config": {
                 "workload": args.workload, "grid": grid_n, "sh_degree": deg, "image": [side, side], "samples_per_ray": spp,
                 "rays_per_gpu_per_step": n_rays, "ray_order": "flat" if args.flat_order else "image(8x4 tiles)",
-                "perturb": not args.no_perturb, "step": "render_rays fwd + l1_loss + backward (grad zero-fill + fused bwd)"
-                + ((" + NCCL all-reduce(grid grad)" if reducer is None else " + in-switch NVLS all-reduce(grid grad)") if world > 1 else ""),
+                "perturb": not args.no_perturb, "step": step_desc, "optimizer": opt_name, "adam_lr": None if args.no_optimizer else args.lr,
+                "exchange": exchange,
                 "l2": f"inputs exceed L2: the grid is {grid_n**3 * rec_bytes / 1e6:.0f} MB vs 126 MB",
                 "variant": args.variant,
             },
+            "phases_ms": {"render_fwd_kernel": fwd_ms, "render_bwd_kernel": bwd_ms, "exchange_plus_optimizer": opt_ms,
+                          "zero_fill_loss_and_launch_gaps": max(0.0, ms_per_step - fwd_ms - bwd_ms - opt_ms)},
+            "collective_ms": opt_ms if world > 1 else 0.0,
+            "fwd_bwd_only": {"ms": ms_per_step - opt_ms, "rays_per_s": world * n_rays / ((ms_per_step - opt_ms) * 1e-3),
+                             "note": "the same timed steps minus the exchange + optimizer phase (round-1 definition at N = 1)"},
             "e2e": {"value": world * n_rays * args.steps / (e2e_ms * 1e-3), "unit": "rays/s",
                     "h2d_bytes_per_step": 3 * n_rays * 12, "d2h_bytes_per_step": n_rays * 12 + 4},
             "gpu_launches": gpu_launches,
-            **roofline_entries(bytes_fwd, fwd_ms, bytes_bwd, bwd_ms, peak, peak_src, traffic_fwd, traffic_bwd),
-            "unique_voxels_touched": touched, "voxel_record_bytes": rec_bytes,
-            "clocks": clocks.summary(),
+            **roofline_entries(bytes_fwd, fwd_ms, bytes_bwd, bwd_ms, peak, peak_src, load_traffic(args.workload), stats, rec_bytes, nf, sm_mhz),
+            "unique_voxels_touched": touched, "voxel_record_bytes": rec_bytes, "sample_statistics": stats,
+            "peak_memory_gb": peak_mem_gb,
+            "clocks": clock_summary,
         }
-        if world == 1 and not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
-            del vol_mod, voxel_grid, params
+        if parity is not None:
+            line["parity_check"] = parity
+        if world == 1:
+            del vol_mod, voxel_grid, params, local_opt
             torch.cuda.empty_cache()
-            rps, mean_s, sample = cpu_oracle_rays_per_sec(args.workload, args.cpu_sample_rays, steps=2, warmup=1, threads=threads)
-            line["cpu_baseline"] = {"value": rps, "unit": "rays/s", "cores": threads, "kind": "port",
-                                    "sample": f"{sample} strided rays of the same {side}x{side} view, fwd+bwd, {mean_s:.2f} s per pass"}
+            if not args.no_gpu_baseline:
+                try:
+                    line["pytorch_gpu_baseline"] = pytorch_gpu_baseline(args.workload, device)
+                except Exception as e:  # noqa: BLE001  (informational row: never fail the bench line)
+                    line["pytorch_gpu_baseline"] = {"unavailable": repr(e)[:200]}
+                torch.cuda.empty_cache()
+            if not args.no_cpu_baseline:
+                threads = os.cpu_count() or 1
+                rps, mean_s, sample, adam_s = cpu_oracle_rays_per_sec(args.workload, args.cpu_sample_rays, steps=2, warmup=1, threads=threads,
+                                                                      with_optimizer=not args.no_optimizer)
+                line["cpu_baseline"] = {"value": rps, "unit": "rays/s", "cores": threads, "kind": "port",
+                                        "sample": f"{sample} strided rays of the same {side}x{side} view, fwd+bwd, {mean_s:.2f} s per pass, extrapolated "
+                                                  f"to the {n_rays}-ray batch, + one dense torch.optim.Adam step over the grid ({adam_s:.2f} s)"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

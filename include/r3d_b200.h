@@ -218,6 +218,21 @@ R3D_API int r3d_adam_step(float* param, const float* grad, float* exp_avg, float
 R3D_API int r3d_multimem_all_reduce(void* multicast_ptr, int64_t num_floats, int32_t rank, int32_t world_size,
                                     int32_t num_blocks, void* cuda_stream);
 
+/* Fused exchange + optimizer over NVLink/NVSwitch: reduce-scatter -> shard-local Adam -> all-gather in one kernel
+ * (replaces the gradient all-reduce followed by optimizer.step() of reference modules/trainers.py:339-341 with the Adam of
+ * :242-245).  `grad_multicast_ptr` / `param_multicast_ptr`: multicast addresses of the flat gradient / parameter buffers,
+ * each allocated symmetrically on all ranks and bound to one multicast object; `param_local`: this rank's own replica of the
+ * parameters.  Rank r owns slice r of r3d_multimem_shard_floats(num_floats, world_size) floats (the last slice may be
+ * shorter): it pulls the summed gradient of the slice (multimem.ld_reduce), updates the slice with its shard of the
+ * optimizer state (`exp_avg_shard`, `exp_avg_sq_shard`: that many floats, kept by the caller between steps) and broadcasts
+ * the new parameters to every replica (multimem.st).  Adam semantics and bias corrections as in r3d_adam_step.  The caller
+ * brackets the call with cross-rank barriers on the same stream.  num_blocks <= 0 picks 2 CTAs per SM. */
+R3D_API int64_t r3d_multimem_shard_floats(int64_t num_floats, int32_t world_size);
+R3D_API int r3d_multimem_adam_step(void* grad_multicast_ptr, void* param_multicast_ptr, const float* param_local, float* exp_avg_shard,
+                                   float* exp_avg_sq_shard, int64_t num_floats, int32_t rank, int32_t world_size, float lr,
+                                   float beta1, float beta2, float eps, float bias_correction1, float bias_correction2,
+                                   float grad_scale, int32_t num_blocks, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

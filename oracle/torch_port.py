@@ -125,8 +125,8 @@ def aabb_ray_bounds(origins, directions, near: float, far: float, aabb) -> torch
     camera near/far.
     """
     n = origins.shape[0]
-    cam = torch.tensor([near, far], dtype=origins.dtype).reshape(1, 2).repeat(n, 1)
-    hit = torch.ones(n, dtype=torch.bool)
+    cam = torch.tensor([near, far], dtype=origins.dtype, device=origins.device).reshape(1, 2).repeat(n, 1)
+    hit = torch.ones(n, dtype=torch.bool, device=origins.device)
     lo = hi = None
     for axis, (a_lo, a_hi) in enumerate(aabb):
         denom = directions[:, axis] + ZERO_PLUS
@@ -151,6 +151,7 @@ def sample_depths(
     near,
     far,
     jitter: Optional[torch.Tensor],
+    device=None,
 ) -> torch.Tensor:
     """Depths ``z[N, S]``.  rendering/volumetric/sample.py:38-64.
 
@@ -159,9 +160,9 @@ def sample_depths(
     means ``perturb=False``.
     """
     if not torch.is_tensor(near):
-        near = torch.tensor([near], dtype=torch.float32).repeat(num_rays, 1)
-        far = torch.tensor([far], dtype=torch.float32).repeat(num_rays, 1)
-    t = torch.linspace(0.0, 1.0, num_samples, dtype=torch.float32)[None, :]
+        near = torch.tensor([near], dtype=torch.float32, device=device).repeat(num_rays, 1)
+        far = torch.tensor([far], dtype=torch.float32, device=device).repeat(num_rays, 1)
+    t = torch.linspace(0.0, 1.0, num_samples, dtype=torch.float32, device=near.device)[None, :]
     z = near * (1.0 - t) + far * t
     if jitter is not None:
         mid = 0.5 * (z[..., 1:] + z[..., :-1])
@@ -195,7 +196,7 @@ def grid_lookup(grid: OracleGrid, points: torch.Tensor) -> torch.Tensor:
 
 def inside_mask(grid: OracleGrid, points: torch.Tensor) -> torch.Tensor:
     """Strict ``lo < p < hi`` on every axis.  voxels.py:252-274."""
-    m = torch.ones(points.shape[0], dtype=torch.bool)
+    m = torch.ones(points.shape[0], dtype=torch.bool, device=points.device)
     for axis, (lo, hi) in enumerate(grid.aabb):
         m = m & (points[:, axis] > lo) & (points[:, axis] < hi)
     return m[:, None]
@@ -247,7 +248,7 @@ def composite(raw_radiance, sigma, depths, directions, white_bkgd: bool, noise=N
     if noise is not None:
         sigma = sigma + noise
     alpha = 1.0 - torch.exp(-(sigma * deltas))
-    ones = torch.ones((alpha.shape[0], 1), dtype=alpha.dtype)
+    ones = torch.ones((alpha.shape[0], 1), dtype=alpha.dtype, device=alpha.device)
     weights = alpha * torch.cumprod(torch.cat([ones, 1.0 - alpha], -1), -1)[:, :-1]
     colour = torch.sum(torch.sigmoid(raw_radiance) * weights[..., None], dim=-2)
     acc = torch.sum(weights, dim=-1, keepdim=True)
@@ -276,9 +277,9 @@ def render(
     n = origins.shape[0]
     if optimized_sampling:
         b = aabb_ray_bounds(origins, directions, near, far, grid.aabb)
-        z = sample_depths(n, num_samples, b[:, :1], b[:, 1:], jitter)
+        z = sample_depths(n, num_samples, b[:, :1], b[:, 1:], jitter, device=origins.device)
     else:
-        z = sample_depths(n, num_samples, near, far, jitter)
+        z = sample_depths(n, num_samples, near, far, jitter, device=origins.device)
     points = origins[:, None, :] + directions[:, None, :] * z[..., None]  # sample.py:67
     flat = points.reshape(-1, 3)
 

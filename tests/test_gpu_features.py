@@ -483,7 +483,11 @@ def test_cooperative_and_per_ray_kernels_agree(name, cuda_device, monkeypatch):
     results = {}
     for label, variant, cache_limit in (("group+cache", 0, None), ("per-ray+cache", 3, None), ("group", 0, "0"), ("per-ray", 3, "0"),
                                         ("staged+cache", 8, None), ("staged", 8, "0"), ("staged, TMA", 4, None),
-                                        ("ws+cache", 32, None), ("ws", 32, "0"), ("ws-sort+cache", 96, None), ("ws, no quads", 32, None)):
+                                        ("ws+cache", 32, None), ("ws", 32, "0"), ("ws-sort+cache", 96, None), ("ws, no quads", 32, None),
+                                        ("ws-sort+L2 prefetch", 96 | 256, None), ("ws-sort+L1 prefetch", 96 | 512, None),
+                                        ("group fwd, ws bwd", 128, None), ("ws fwd, ws bwd", 96 | 128, None),
+                                        ("group-sort+cache", 2048, None), ("group-sort", 2048, "0"),
+                                        ("ws-sort+dual streams", 96 | 1024, None), ("ws-sort+L2 prefetch+dual streams", 96 | 256 | 1024, None)):
         if cache_limit is None:
             monkeypatch.delenv("R3D_SAMPLE_CACHE_MAX_BYTES", raising=False)
         else:

@@ -393,11 +393,37 @@ def test_bench_reports_the_dominant_kernel_in_the_roofline_entry():
     spec = importlib.util.spec_from_file_location("r3d_bench", Path(__file__).resolve().parent.parent / "bench.py")
     bench = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(bench)
-    r = bench.roofline_entries(1_500_000_000, 4.5, 4_500_000_000, 4.4, 6500.0, "measured", 3, 5)
+    stats = {"samples_visited": 1000, "samples_inside": 600, "corner_refs": 4700, "samples_contributing": 300}
+    traffic = {"render_fwd_dram_bytes": 3, "render_bwd_dram_bytes": 5, "source": "ncu"}
+    r = bench.roofline_entries(1_500_000_000, 4.5, 4_500_000_000, 4.4, 6500.0, "measured", traffic, stats, 112, 27, 1965.0)
     assert r["roofline"]["kernel"] == "render_fwd_group_kernel" and r["roofline"] == r["roofline_fwd"]
     assert r["roofline_bwd"]["traffic"] == 5 and r["roofline_fwd"]["traffic"] == 3
     assert abs(r["roofline_bwd"]["achieved"] - 4.5e9 / 4.4e-3 / 1e9) < 1e-6 and abs(r["roofline_bwd"]["frac"] - r["roofline_bwd"]["achieved"] / 6500.0) < 1e-12
-    r = bench.roofline_entries(1_500_000_000, 4.0, 4_500_000_000, 4.4, 6500.0, "measured")
+    # SURVEY.md 8d companion figures travel with every entry: gather-request bytes and the FP32 work against the SIMT peak
+    assert r["roofline_fwd"]["gather_request_bytes"] == 4700 * 112
+    assert abs(r["roofline_fwd"]["fp32_peak_tflops"] - 148 * 128 * 2 * 1.965e9 / 1e12) < 1e-9
+    assert 0.0 < r["roofline_fwd"]["fp32_frac"] < 1.0 and r["roofline_fwd"]["fp32_flops"] > r["roofline_bwd"]["fp32_flops"] * 0.5
+    r = bench.roofline_entries(1_500_000_000, 4.0, 4_500_000_000, 4.4, 6500.0, "measured", {"source": "stale"}, stats, 112, 27, 1965.0)
     assert r["roofline"]["kernel"] == "render_bwd_coop_kernel" and r["roofline"]["traffic"] is None
     for key in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
         assert key in r["roofline"]
+
+
+def test_bench_refuses_stale_dram_traffic_numbers(tmp_path, monkeypatch):
+    """profiles/traffic.json is stamped with the digest of the library sources it was measured with; any other digest => null."""
+    import importlib.util
+    import json
+    from pathlib import Path
+
+    spec = importlib.util.spec_from_file_location("r3d_bench2", Path(__file__).resolve().parent.parent / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    from thr3ed_atom_b200 import build as _build
+
+    (tmp_path / "profiles").mkdir()
+    monkeypatch.setattr(bench, "ROOT", tmp_path)
+    path = tmp_path / "profiles" / "traffic.json"
+    path.write_text(json.dumps({"lib_digest": "not-the-current-sources", "w": {"render_fwd_dram_bytes": 1}}))
+    assert "render_fwd_dram_bytes" not in bench.load_traffic("w") and "stale" in bench.load_traffic("w")["source"]
+    path.write_text(json.dumps({"lib_digest": _build._source_digest(), "measured": "r02", "w": {"render_fwd_dram_bytes": 1, "render_bwd_dram_bytes": 2}}))
+    assert bench.load_traffic("w")["render_fwd_dram_bytes"] == 1 and bench.load_traffic("w")["render_bwd_dram_bytes"] == 2

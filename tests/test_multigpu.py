@@ -72,3 +72,79 @@ def test_nvls_gradient_all_reduce_matches_nccl(tmp_path):
         port = s.getsockname()[1]
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+
+
+def _sharded_adam_worker(rank, world, port, tmp):
+    import torch.distributed as dist
+
+    from helpers import CASES, build_inputs, make_cuda_config, make_cuda_grid
+    from thr3ed_atom_b200.distributed import NVLSShardedAdam, all_reduce_grid_gradients, shard_rays
+    from thr3ed_atom_b200.rendering.volumetric.render_interface import Rays
+    from thr3ed_atom_b200.thre3d_reprs.renderers import render_sh_voxel_grid
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        case = CASES["deg2_16cube"]
+        inp = build_inputs(case)
+        rays = Rays(torch.from_numpy(inp["origins"]).to(dev), torch.from_numpy(inp["directions"]).to(dev))
+        gc = torch.from_numpy(inp["grad_colour"]).to(dev)
+        shard = shard_rays(rays, gc)
+        lr = 0.03
+
+        def local_backward(grid):
+            out = render_sh_voxel_grid(grid, shard.rays, make_cuda_config(case))
+            (out.colour * shard.pixels).sum().backward()
+
+        # reference: NCCL all-reduce of autograd gradients, then torch.optim.Adam on every rank
+        grid_a = make_cuda_grid(case, inp, dev)
+        opt_a = torch.optim.Adam([{"params": list(grid_a.parameters()), "lr": lr}], betas=(0.9, 0.999))
+        # fused: reduce-scatter -> shard-local Adam -> all-gather inside the switch
+        grid_b = make_cuda_grid(case, inp, dev)
+        before = [p.detach().clone() for p in grid_b.parameters()]
+        opt_b = NVLSShardedAdam(grid_b, lr=lr, betas=(0.9, 0.999))
+        for p, b in zip(grid_b.parameters(), before):
+            assert torch.equal(p.detach(), b)  # re-homing keeps the values
+        assert opt_b.state["exp_avg"].numel() * world >= opt_b.total  # 1/n of the optimizer state per GPU
+        assert opt_b.state["exp_avg"].numel() <= opt_b.total // world + 4
+        for step in range(3):
+            opt_a.zero_grad()
+            local_backward(grid_a)
+            all_reduce_grid_gradients(grid_a)
+            opt_a.step()
+            opt_b.zero_grad()
+            local_backward(grid_b)
+            opt_b.step()
+            torch.cuda.synchronize()
+            for pa, pb in zip(grid_a.parameters(), grid_b.parameters()):
+                # Adam's first steps move every touched element by ~lr: compare the updates, not only the values
+                err = float((pa.detach() - pb.detach()).abs().max())
+                assert err < 2e-4 * lr + 1e-6, (step, err)
+        # the replicas stay identical across ranks (every rank received every slice)
+        for pb in grid_b.parameters():
+            mine = pb.detach().clone()
+            other = mine.clone()
+            dist.broadcast(other, src=0)
+            assert torch.equal(mine, other)
+        opt_b.close()
+        torch.save(torch.tensor(1), os.path.join(tmp, f"ok{rank}"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_fused_reduce_scatter_adam_all_gather_matches_all_reduce_plus_adam(tmp_path):
+    """reference modules/trainers.py:339-341 (backward -> optimizer.step) across 2 GPUs: the in-switch fused kernel against
+    NCCL all-reduce + torch.optim.Adam, three steps through the real render path."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import socket
+
+    import torch.multiprocessing as mp
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_sharded_adam_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()

@@ -108,6 +108,11 @@ SIGNATURES = {
     "r3d_density_quad_floats": (C.c_int64, [C.POINTER(C.c_int32 * 3)]),
     "r3d_build_density_quads": (C.c_int, [C.POINTER(R3dGrid), C.c_void_p, C.c_void_p]),
     "r3d_multimem_all_reduce": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "r3d_multimem_shard_floats": (C.c_int64, [C.c_int64, C.c_int32]),
+    "r3d_multimem_adam_step": (
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32] + [C.c_float] * 7 + [C.c_int32, C.c_void_p],
+    ),
     "r3d_adam_step": (
         C.c_int,
         [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64] + [C.c_float] * 7 + [C.c_void_p],

@@ -195,7 +195,7 @@ def sample_mask_supported(grid: GridDesc, args: RenderArgs) -> bool:
     the backward use them (ReLU density post-activation)?  Mirrors ``fwd_uses_group_kernel`` / ``mask_usable`` in
     ``csrc/r3d_render.cu``; the library refuses a mask it would not write."""
     f = grid.features
-    return ((args.variant & ~96) == 0 and not args.diffuse and grid.density_post == _abi.POST_RELU and f.shape[3] % 4 == 0
+    return ((args.variant & ~(96 | 128 | 256 | 512 | 1024 | 2048)) == 0 and not args.diffuse and grid.density_post == _abi.POST_RELU and f.shape[3] % 4 == 0
             and f.data_ptr() % 16 == 0 and f.shape[0] * f.shape[1] * f.shape[2] * (f.shape[3] // 4) <= 0xFFFFFFFF)
 
 
@@ -356,4 +356,34 @@ def multimem_all_reduce(multicast_ptr: int, num_floats: int, rank: int, world_si
         _abi.check(
             _abi.lib().r3d_multimem_all_reduce(C.c_void_p(multicast_ptr), num_floats, rank, world_size, num_blocks, _stream(device)),
             "r3d_multimem_all_reduce",
+        )
+
+
+def multimem_shard_floats(num_floats: int, world_size: int) -> int:
+    n = int(_abi.lib().r3d_multimem_shard_floats(num_floats, world_size))
+    if n < 0:
+        raise ValueError("flat buffer must be a non-negative multiple of 4 floats")
+    return n
+
+
+def multimem_adam_step(grad_multicast_ptr: int, param_multicast_ptr: int, param_local: Tensor, exp_avg_shard: Tensor, exp_avg_sq_shard: Tensor,
+                       rank: int, world_size: int, *, lr: float, beta1: float, beta2: float, eps: float, step: int, grad_scale: float = 1.0,
+                       num_blocks: int = 0) -> None:
+    """Enqueue the fused reduce-scatter -> shard-local Adam -> all-gather kernel (see ``r3d_multimem_adam_step``)."""
+    for name, t in (("param_local", param_local), ("exp_avg_shard", exp_avg_shard), ("exp_avg_sq_shard", exp_avg_sq_shard)):
+        _require_cuda(t, name)
+        if not t.is_contiguous():
+            raise ValueError(f"{name} must be contiguous")
+    shard = multimem_shard_floats(param_local.numel(), world_size)
+    if exp_avg_shard.numel() != shard or exp_avg_sq_shard.numel() != shard:
+        raise ValueError(f"optimizer state shards must hold {shard} floats")
+    device = param_local.device
+    with torch.cuda.device(device):
+        _abi.check(
+            _abi.lib().r3d_multimem_adam_step(
+                C.c_void_p(grad_multicast_ptr), C.c_void_p(param_multicast_ptr), param_local.data_ptr(), exp_avg_shard.data_ptr(),
+                exp_avg_sq_shard.data_ptr(), param_local.numel(), rank, world_size, lr, beta1, beta2, eps, 1.0 - beta1**step,
+                1.0 - beta2**step, grad_scale, num_blocks, _stream(device),
+            ),
+            "r3d_multimem_adam_step",
         )

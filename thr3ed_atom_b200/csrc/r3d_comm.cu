@@ -49,9 +49,122 @@ __global__ void __launch_bounds__(512) multimem_allreduce_kernel(float* __restri
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Fused exchange + optimizer: reduce-scatter -> shard-local Adam -> all-gather in ONE kernel (replaces
+// the all-reduce followed by torch.optim.Adam.step of reference modules/trainers.py:339-341, :242-245).
+//
+// Rank r owns slice r of the flat parameter vector.  For every 16 bytes of its slice it
+//   1. pulls the SUM over all ranks of the gradient  (multimem.ld_reduce on the gradient's multicast address: the NVSwitch
+//      reads the n replicas and returns one reduced value),
+//   2. applies Adam with ITS shard of the optimizer state (exp_avg / exp_avg_sq exist once per box, 1/n per GPU),
+//   3. pushes the updated PARAMETERS to every replica      (multimem.st on the parameters' multicast address).
+// The reduced gradient is never written anywhere; per GPU and direction ~1x the gradient bytes cross NVLink, the dense
+// 7-streams-per-element optimizer pass over the whole grid disappears from every GPU, and so do 7/8 of its state.
+// The caller brackets the launch with cross-rank barriers (all gradients complete before; all parameters updated after).
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) multimem_adam_kernel(const float* __restrict__ grad_mc, float* __restrict__ param_mc,
+                                                            const float* __restrict__ param_local, float* __restrict__ m, float* __restrict__ v,
+                                                            long long vec_begin, long long vec_end, float step, float b1, float b2, float eps,
+                                                            float bc2_sqrt, float gscale) {
+  constexpr int UNROLL = 4;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  auto update = [&](const float4& G, float4& P, float4& M, float4& V) {
+#define R3D_ADAM1(c)                                       \
+  {                                                        \
+    const float gg = G.c * gscale;                         \
+    M.c = fmaf(b1, M.c, (1.0f - b1) * gg);                 \
+    V.c = fmaf(b2, V.c, (1.0f - b2) * gg * gg);            \
+    P.c -= step * (M.c / (sqrtf(V.c) / bc2_sqrt + eps));   \
+  }
+    R3D_ADAM1(x) R3D_ADAM1(y) R3D_ADAM1(z) R3D_ADAM1(w)
+#undef R3D_ADAM1
+  };
+  long long i = vec_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + (UNROLL - 1) * stride < vec_end; i += UNROLL * stride) {
+    float4 G[UNROLL], P[UNROLL], M[UNROLL], V[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const long long j = i + u * stride;
+      asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(G[u].x), "=f"(G[u].y), "=f"(G[u].z), "=f"(G[u].w)
+                   : "l"(grad_mc + 4 * j)
+                   : "memory");
+      P[u] = *reinterpret_cast<const float4*>(param_local + 4 * j);
+      M[u] = reinterpret_cast<const float4*>(m)[j - vec_begin];
+      V[u] = reinterpret_cast<const float4*>(v)[j - vec_begin];
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const long long j = i + u * stride;
+      update(G[u], P[u], M[u], V[u]);
+      asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(param_mc + 4 * j), "f"(P[u].x), "f"(P[u].y),
+                   "f"(P[u].z), "f"(P[u].w)
+                   : "memory");
+      reinterpret_cast<float4*>(m)[j - vec_begin] = M[u];
+      reinterpret_cast<float4*>(v)[j - vec_begin] = V[u];
+    }
+  }
+  for (; i < vec_end; i += stride) {
+    float4 G, P, M, V;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(G.x), "=f"(G.y), "=f"(G.z), "=f"(G.w)
+                 : "l"(grad_mc + 4 * i)
+                 : "memory");
+    P = *reinterpret_cast<const float4*>(param_local + 4 * i);
+    M = reinterpret_cast<const float4*>(m)[i - vec_begin];
+    V = reinterpret_cast<const float4*>(v)[i - vec_begin];
+    update(G, P, M, V);
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(param_mc + 4 * i), "f"(P.x), "f"(P.y), "f"(P.z), "f"(P.w)
+                 : "memory");
+    reinterpret_cast<float4*>(m)[i - vec_begin] = M;
+    reinterpret_cast<float4*>(v)[i - vec_begin] = V;
+  }
+}
+
+// slice of rank `rank`, in float4 units: the same partition for the all-reduce and for the fused optimizer
+static void slice_of(long long vecs, int rank, int world, long long& begin, long long& end) {
+  const long long per = (vecs + world - 1) / world;
+  begin = per * rank;
+  end = begin + per < vecs ? begin + per : vecs;
+  if (begin > vecs) begin = end = vecs;
+}
+
 }  // namespace r3d
 
 using namespace r3d;
+
+extern "C" int64_t r3d_multimem_shard_floats(int64_t num_floats, int32_t world_size) {
+  if (num_floats < 0 || (num_floats % 4) != 0 || world_size < 1) return -1;
+  const long long vecs = num_floats / 4;
+  return 4 * ((vecs + world_size - 1) / world_size);
+}
+
+extern "C" int r3d_multimem_adam_step(void* grad_multicast_ptr, void* param_multicast_ptr, const float* param_local, float* exp_avg_shard,
+                                      float* exp_avg_sq_shard, int64_t num_floats, int32_t rank, int32_t world_size, float lr, float beta1,
+                                      float beta2, float eps, float bias_correction1, float bias_correction2, float grad_scale,
+                                      int32_t num_blocks, void* cuda_stream) {
+  if (!grad_multicast_ptr || !param_multicast_ptr)
+    return fail(R3D_ERR_INVALID_ARGUMENT, "r3d_multimem_adam_step: multicast pointer is NULL (no NVLS multicast mapping)");
+  if (!param_local || !exp_avg_shard || !exp_avg_sq_shard) return fail(R3D_ERR_INVALID_ARGUMENT, "r3d_multimem_adam_step: NULL argument");
+  if (world_size < 1 || rank < 0 || rank >= world_size) return fail(R3D_ERR_INVALID_ARGUMENT, "r3d_multimem_adam_step: bad rank/world_size");
+  if (num_floats < 0 || (num_floats % 4) != 0 || !aligned16(grad_multicast_ptr) || !aligned16(param_multicast_ptr) || !aligned16(param_local) ||
+      !aligned16(exp_avg_shard) || !aligned16(exp_avg_sq_shard))
+    return fail(R3D_ERR_INVALID_ARGUMENT, "r3d_multimem_adam_step: buffers must be 16-byte aligned and a multiple of 4 floats");
+  if (!(bias_correction1 > 0.f) || !(bias_correction2 > 0.f)) return fail(R3D_ERR_INVALID_ARGUMENT, "r3d_multimem_adam_step: bias corrections must be positive");
+  long long begin, end;
+  slice_of(num_floats / 4, rank, world_size, begin, end);
+  if (begin >= end) return R3D_OK;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int blocks = num_blocks > 0 ? num_blocks : sms * 2;
+  const long long need = (end - begin + 511) / 512;
+  if (blocks > need) blocks = (int)need;
+  multimem_adam_kernel<<<blocks, 512, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+      static_cast<const float*>(grad_multicast_ptr), static_cast<float*>(param_multicast_ptr), param_local, exp_avg_shard, exp_avg_sq_shard, begin,
+      end, lr / bias_correction1, beta1, beta2, eps, sqrtf(bias_correction2), grad_scale);
+  return check_launch("r3d_multimem_adam_step");
+}
 
 extern "C" int r3d_multimem_all_reduce(void* multicast_ptr, int64_t num_floats, int32_t rank, int32_t world_size, int32_t num_blocks,
                                        void* cuda_stream) {
@@ -59,9 +172,8 @@ extern "C" int r3d_multimem_all_reduce(void* multicast_ptr, int64_t num_floats, 
   if (world_size < 1 || rank < 0 || rank >= world_size) return fail(R3D_ERR_INVALID_ARGUMENT, "r3d_multimem_all_reduce: bad rank/world_size");
   if (num_floats < 0 || (num_floats % 4) != 0 || !aligned16(multicast_ptr))
     return fail(R3D_ERR_INVALID_ARGUMENT, "r3d_multimem_all_reduce: buffer must be 16-byte aligned and a multiple of 4 floats");
-  const long long vecs = num_floats / 4;
-  const long long per = (vecs + world_size - 1) / world_size;
-  const long long begin = per * rank, end = begin + per < vecs ? begin + per : vecs;
+  long long begin, end;
+  slice_of(num_floats / 4, rank, world_size, begin, end);
   if (begin >= end) return R3D_OK;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);

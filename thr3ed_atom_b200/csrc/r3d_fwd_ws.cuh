@@ -25,14 +25,24 @@
 #ifndef R3D_WS_BLOCKS
 #define R3D_WS_BLOCKS 3
 #endif
+#ifndef R3D_WS_BLOCKS_DQ
+#define R3D_WS_BLOCKS_DQ 2
+#endif
+#ifndef R3D_WS_STAGES
+#define R3D_WS_STAGES 4
+#endif
+#ifndef R3D_WS_LAG
+#define R3D_WS_LAG 3
+#endif
 #ifndef R3D_WS_FFMA2
 #define R3D_WS_FFMA2 1
 #endif
 
 namespace r3d {
 
-constexpr int kWsStages = 3;  // ring depth per producer/consumer pair
-constexpr int kWsLag = 2;     // the producer composites stage p - kWsLag after publishing stage p (must be < kWsStages)
+constexpr int kWsStages = R3D_WS_STAGES;  // ring depth per producer/consumer pair
+constexpr int kWsLag = R3D_WS_LAG;        // the producer composites stage p - kWsLag after publishing stage p
+static_assert(kWsLag < kWsStages, "a stage must have been composited before it is published again");
 
 // Bounded wait: a protocol bug must surface as a CUDA error (trap), never as a hung GPU.  try_wait suspends the warp in
 // hardware for up to a system-dependent time per attempt, so the bound is generous (seconds).
@@ -50,6 +60,19 @@ __device__ __forceinline__ void mbar_wait_bounded(unsigned long long* bar, unsig
     if (ok) return;
     if (spin > (1u << 24)) __trap();
   }
+}
+
+// one non-blocking probe of a phase
+__device__ __forceinline__ bool mbar_test(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity)
+      : "memory");
+  return ok != 0u;
 }
 
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
@@ -115,8 +138,11 @@ struct DepthTab {
 
 // SORT: the producer publishes the contributing samples grouped by interpolation cell (__match_any_sync on the cell key +
 // a warp scan of the group sizes) instead of in lane order, so that every distinct cell of a marching step is one run.
-template <int DEG, bool DUAL, bool SORT>
-__global__ void __launch_bounds__(256, DEG >= 3 ? 2 : R3D_WS_BLOCKS)
+// PF: the producer prefetches the published samples' corner records (1 = into L2, 2 = into L1) kWsLag stages before the
+// consumer gathers them.
+// DQ: the consumer gathers for two stages at a time (two record register sets per lane).
+template <int DEG, bool DUAL, bool SORT, int PF, bool DQ>
+__global__ void __launch_bounds__(256, DEG >= 3 ? 2 : (DQ ? R3D_WS_BLOCKS_DQ : R3D_WS_BLOCKS))
     render_fwd_ws_kernel(const GridP g, const RaysP rp, const CfgP c, const OutP out, const int use_tab) {
   using H = FwdGroupShape<DEG>;
   using S = CoopShape<DEG>;
@@ -177,74 +203,124 @@ __global__ void __launch_bounds__(256, DEG >= 3 ? 2 : R3D_WS_BLOCKS)
     for (int ch = 0; ch < 3; ++ch)
       if (DUAL && DEG > 0 && cj == (ch * K) / 4) dslot = ch, dcomp = (ch * K) % 4;
 
-    int gs = 0;
-    unsigned gpar = 0u;
-    float4 q[8];
+    // load(): V row of sample m; when it names another cell than the one held in q[], request its 8 corner records
+    auto load = [&](WsStage<DUAL>& st, int m, bool on, float4(&q)[8], unsigned& key0, unsigned& key7) {
+      if (!on) return;
+      const uint4 v0 = st.Vlo[m], v1 = st.Vhi[m];
+      if (v0.x != key0 || v1.w != key7) {  // corners 0 and 7 identify the cell (low and high voxel of every axis)
+        key0 = v0.x, key7 = v1.w;
+        const unsigned vk[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
-    for (int k = 0; k < 8; ++k) q[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    unsigned key0 = 0xffffffffu, key7 = 0xffffffffu;  // corner-0 / corner-7 record of the cell held in q[] (the grid is read-only)
-    while (true) {
-      WsStage<DUAL>& st = sm.st[gs];
-      mbar_wait_bounded(&sm.full[gs], gpar);
-      const int n = st.n;
-      if (n < 0) break;
-      const int chunk = (n + MPI - 1) / MPI;
-      const int m_end = min(n, (ms + 1) * chunk);
-      for (int it = 0; it < chunk; ++it) {
-        const int m = ms * chunk + it;
-        const bool on = m < m_end && role_ok;
-        float2 a01 = make_float2(0.f, 0.f), a23 = make_float2(0.f, 0.f);
-        if (on) {
-          const uint4 v0 = st.Vlo[m], v1 = st.Vhi[m];
-          if (v0.x != key0 || v1.w != key7) {  // corners 0 and 7 identify the cell (low and high voxel of every axis)
-            key0 = v0.x, key7 = v1.w;
-            const unsigned vk[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {  // address = lane base + 16 * record index
-              unsigned long long addr;
-              asm("mad.wide.u32 %0, %1, 16, %2;" : "=l"(addr) : "r"(vk[k]), "l"(feat_lane));
-              q[k] = __ldg(reinterpret_cast<const float4*>(addr));
-            }
-          }
-          const float4 w0 = st.Wlo[m], w1 = st.Whi[m];
-          float4 y4;
-          lds_v4(y_lane + st.yoff[m], y4.x, y4.y, y4.z, y4.w);
-          const float wk[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            a01 = ffma2(make_float2(q[k].x, q[k].y), wk[k], a01);
-            a23 = ffma2(make_float2(q[k].z, q[k].w), wk[k], a23);
-          }
-          if constexpr (DUAL && DEG > 0) {  // band-0 radiance: C0 * interpolated coeff[ch][0]
-            if (dslot >= 0)
-              reinterpret_cast<float*>(&st.R2[m])[dslot] = 0.28209479177387814f * (dcomp == 0 ? a01.x : (dcomp == 1 ? a01.y : (dcomp == 2 ? a23.x : a23.y)));
-          }
-          a01.x *= y4.x, a01.y *= y4.y, a23.x *= y4.z, a23.y *= y4.w;  // the pad element has Y = 0
-        }
-        if constexpr (DEG == 0) {
-          if (on) st.R[m] = make_float4(a01.x, a01.y, a23.x, a23.y);
-        } else {
-          const float u01 = a01.x + a01.y, u23 = a23.x + a23.y;
-          float v;
-          if constexpr (DEG == 2) {  // see render_fwd_group_kernel: float4s 2 and 4 straddle a channel boundary
-            const float A = split1 ? a01.x : (split2 ? u01 : u01 + u23);
-            const float B = split1 ? a01.y + u23 : (split2 ? u23 : 0.0f);
-            const float x = __shfl_xor_sync(FULL, odd ? A : B, 1);
-            v = (split1 || split2) ? A : A + x;
-            v += __shfl_sync(FULL, v, trade_lane);
-          } else {
-            v = u01 + u23;
-            if constexpr (DEG == 3) {
-              v += __shfl_xor_sync(FULL, v, 1);
-              v += __shfl_xor_sync(FULL, v, 2);
-            }
-          }
-          if (on && out_slot >= 0) reinterpret_cast<float*>(&st.R[m])[out_slot] = v;
+        for (int k = 0; k < 8; ++k) {  // address = lane base + 16 * record index
+          unsigned long long addr;
+          asm("mad.wide.u32 %0, %1, 16, %2;" : "=l"(addr) : "r"(vk[k]), "l"(feat_lane));
+          q[k] = __ldg(reinterpret_cast<const float4*>(addr));
         }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.done[gs]);
-      if (++gs == NS) gs = 0, gpar ^= 1u;
+    };
+    // maths(): weights, SH row, channel sums of the group -> raw radiance of sample m (executed by every lane: shuffles)
+    auto maths = [&](WsStage<DUAL>& st, int m, bool on, const float4(&q)[8]) {
+      float2 a01 = make_float2(0.f, 0.f), a23 = make_float2(0.f, 0.f);
+      if (on) {
+        const float4 w0 = st.Wlo[m], w1 = st.Whi[m];
+        float4 y4;
+        lds_v4(y_lane + st.yoff[m], y4.x, y4.y, y4.z, y4.w);
+        const float wk[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          a01 = ffma2(make_float2(q[k].x, q[k].y), wk[k], a01);
+          a23 = ffma2(make_float2(q[k].z, q[k].w), wk[k], a23);
+        }
+        if constexpr (DUAL && DEG > 0) {  // band-0 radiance: C0 * interpolated coeff[ch][0]
+          if (dslot >= 0)
+            reinterpret_cast<float*>(&st.R2[m])[dslot] = 0.28209479177387814f * (dcomp == 0 ? a01.x : (dcomp == 1 ? a01.y : (dcomp == 2 ? a23.x : a23.y)));
+        }
+        a01.x *= y4.x, a01.y *= y4.y, a23.x *= y4.z, a23.y *= y4.w;  // the pad element has Y = 0
+      }
+      if constexpr (DEG == 0) {
+        if (on) st.R[m] = make_float4(a01.x, a01.y, a23.x, a23.y);
+      } else {
+        const float u01 = a01.x + a01.y, u23 = a23.x + a23.y;
+        float v;
+        if constexpr (DEG == 2) {  // see render_fwd_group_kernel: float4s 2 and 4 straddle a channel boundary
+          const float A = split1 ? a01.x : (split2 ? u01 : u01 + u23);
+          const float B = split1 ? a01.y + u23 : (split2 ? u23 : 0.0f);
+          const float x = __shfl_xor_sync(FULL, odd ? A : B, 1);
+          v = (split1 || split2) ? A : A + x;
+          v += __shfl_sync(FULL, v, trade_lane);
+        } else {
+          v = u01 + u23;
+          if constexpr (DEG == 3) {
+            v += __shfl_xor_sync(FULL, v, 1);
+            v += __shfl_xor_sync(FULL, v, 2);
+          }
+        }
+        if (on && out_slot >= 0) reinterpret_cast<float*>(&st.R[m])[out_slot] = v;
+      }
+    };
+
+    int gs = 0;
+    unsigned gpar = 0u;
+    float4 qa[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) qa[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    unsigned ka0 = 0xffffffffu, ka7 = 0xffffffffu;  // corner-0 / corner-7 record of the cell held in qa[] (the grid is read-only)
+    if constexpr (DQ) {
+      // Two stages at a time whenever the producer is far enough ahead (it runs kWsLag stages ahead, so almost always): each
+      // group walks one chunk of stage A and one of stage B in the same iteration, with separate record registers, so 16
+      // independent 128-bit loads are in flight per lane before the first is consumed.  The consumer is latency-bound on
+      // exactly those loads (profiles/r02_ws2_*: 40 % of all stall samples sit on their first use).
+      float4 qb[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) qb[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      unsigned kb0 = 0xffffffffu, kb7 = 0xffffffffu;
+      while (true) {
+        WsStage<DUAL>& sa = sm.st[gs];
+        mbar_wait_bounded(&sm.full[gs], gpar);
+        const int na = sa.n;
+        if (na < 0) break;
+        const int gs2 = (gs + 1 == NS) ? 0 : gs + 1;
+        const unsigned gpar2 = (gs + 1 == NS) ? (gpar ^ 1u) : gpar;
+        WsStage<DUAL>& sb = sm.st[gs2];
+        int nb = 0;
+        const bool two = __all_sync(FULL, mbar_test(&sm.full[gs2], gpar2)) && (nb = sb.n) > 0;  // warp-uniform
+        const int ca = (na + MPI - 1) / MPI, cb = two ? (nb + MPI - 1) / MPI : 0;
+        const int ea = min(na, (ms + 1) * ca), eb = min(nb, (ms + 1) * cb);
+        const int iters = max(ca, cb);
+        for (int it = 0; it < iters; ++it) {
+          const int ma = ms * ca + it, mb = ms * cb + it;
+          const bool ona = it < ca && ma < ea && role_ok, onb = it < cb && mb < eb && role_ok;
+          load(sa, ma, ona, qa, ka0, ka7);
+          load(sb, mb, onb, qb, kb0, kb7);
+          maths(sa, ma, ona, qa);
+          if (two) maths(sb, mb, onb, qb);
+        }
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&sm.done[gs]);
+          if (two) mbar_arrive(&sm.done[gs2]);
+        }
+        if (two) gs = gs2, gpar = gpar2;
+        if (++gs == NS) gs = 0, gpar ^= 1u;
+      }
+    } else {
+      while (true) {
+        WsStage<DUAL>& st = sm.st[gs];
+        mbar_wait_bounded(&sm.full[gs], gpar);
+        const int n = st.n;
+        if (n < 0) break;
+        const int chunk = (n + MPI - 1) / MPI;
+        const int m_end = min(n, (ms + 1) * chunk);
+        for (int it = 0; it < chunk; ++it) {
+          const int m = ms * chunk + it;
+          const bool on = m < m_end && role_ok;
+          load(st, m, on, qa, ka0, ka7);
+          maths(st, m, on, qa);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.done[gs]);
+        if (++gs == NS) gs = 0, gpar ^= 1u;
+      }
     }
     return;
   }
@@ -390,6 +466,20 @@ __global__ void __launch_bounds__(256, DEG >= 3 ? 2 : R3D_WS_BLOCKS)
           const int ix = k >> 2, iy = (k >> 1) & 1, iz = k & 1;
           wc[k] = cell.wx[ix] * cell.wy[iy] * cell.wz[iz];
           rec4[k] = (unsigned)(cell.ox[ix] + cell.oy[iy] + cell.oz[iz]) * stride4;
+        }
+        if constexpr (PF != 0) {
+          // a record is F floats at a 16-byte aligned offset: its first and its last byte name the (at most two) 128-byte lines
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const char* rec = reinterpret_cast<const char*>(g.feat) + 16ull * rec4[k];
+            if constexpr (PF == 1) {
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(rec));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + (4 * F - 4)));
+            } else {
+              asm volatile("prefetch.global.L1 [%0];" ::"l"(rec));
+              asm volatile("prefetch.global.L1 [%0];" ::"l"(rec + (4 * F - 4)));
+            }
+          }
         }
         st.Wlo[rank] = make_float4(wc[0], wc[1], wc[2], wc[3]);
         st.Whi[rank] = make_float4(wc[4], wc[5], wc[6], wc[7]);

@@ -601,7 +601,11 @@ struct alignas(16) FwdGroupSmem {  // one per warp
 // modules/trainers.py:306-330 renders every batch twice).  raw_diffuse[ch] = C0 * coeff[ch][0] is the k = 0 element of
 // the record the specular render interpolates anyway: the lanes that hold elements 0, K, 2K hand it over before the SH
 // weighting, everything else (samples, density, weights, depth, acc) is shared.
-template <int DEG, bool DUAL>
+// SORT: publish the contributing samples grouped by interpolation cell instead of in lane order.  Consecutive slots are
+// gathered by DIFFERENT lane groups in the SAME load instruction, and lanes that name the same address are served by
+// one L1 wavefront: a cell shared by several samples of a marching step then crosses the L1 data pipe once per
+// instruction instead of once per sample.
+template <int DEG, bool DUAL, bool SORT = false>
 __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_FWD_BLOCKS) render_fwd_group_kernel(const GridP g, const RaysP rp, const CfgP c, const OutP out) {
   using H = FwdGroupShape<DEG>;
   using S = CoopShape<DEG>;
@@ -697,7 +701,24 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_FWD_BLOCKS) render_fwd
     if (out.mask && lane == 0) out.mask[(size_t)i * (gridDim.x * 4u) + (blockIdx.x * 4u + (threadIdx.x >> 5))] = act;
     if (act != 0u) {
       const int total = __popc(act);
-      const int rank = __popc(act & ((1u << lane) - 1u));
+      int rank = __popc(act & ((1u << lane) - 1u));
+      if constexpr (SORT) {
+        // slot = (samples of cells whose first lane precedes this cell's first lane) + (position among the cell's lanes);
+        // the low and the high voxel of the cell (corners 0 and 7) identify it
+        unsigned peers = 0u;
+        if (contributes)
+          peers = __match_any_sync(act, (unsigned long long)(unsigned)(cell.ox[0] + cell.oy[0] + cell.oz[0]) |
+                                            ((unsigned long long)(unsigned)(cell.ox[1] + cell.oy[1] + cell.oz[1]) << 32));
+        const int leader = contributes ? (__ffs(peers) - 1) : lane;
+        int scan = (contributes && leader == lane) ? __popc(peers) : 0;  // group size at the group's first lane
+        const int own = scan;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int up = __shfl_up_sync(FULL, scan, o);
+          if (lane >= o) scan += up;
+        }
+        rank = __shfl_sync(FULL, scan - own, leader) + __popc(peers & ((1u << lane) - 1u));
+      }
       // ---- publish the sample: 8 corner weights, 8 corner record indices (in float4s; the launcher checked that
       //      they fit 32 bits), owning lane ----
       if (contributes) {
@@ -898,6 +919,10 @@ __device__ __forceinline__ bool load_ray_grad(const BwdP& b, const CfgP& c, long
   rg.total = fmaf(gcd[0], dfr, fmaf(gcd[1], dfg, fmaf(gcd[2], dfb, rg.total)));
   return !(gc[0] == 0.f && gc[1] == 0.f && gc[2] == 0.f && gd == 0.f && ga == 0.f && gcd[0] == 0.f && gcd[1] == 0.f && gcd[2] == 0.f);
 }
+
+}  // namespace r3d
+#include "r3d_bwd_ws.cuh"
+namespace r3d {
 
 // =================================================================================================
 // backward
@@ -1251,9 +1276,9 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : (DUAL ? R3D_BWD_DUAL_BLOCK
       // One sweep over the cell's member samples accumulates, per lane, its float4 of up to PASSES corner records
       // (the P row is loaded once and reused for every pass) and the density gradient of corner (lane & 7).  Every lane
       // runs the sweep (lanes without a role read in-bounds garbage and never store): no divergence inside the loop.
-      float4 a[S::PASSES];
+      float2 a01[S::PASSES], a23[S::PASSES];  // packed pairs: one FFMA2 per two record elements (sm_100)
 #pragma unroll
-      for (int pass = 0; pass < S::PASSES; ++pass) a[pass] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int pass = 0; pass < S::PASSES; ++pass) a01[pass] = a23[pass] = make_float2(0.f, 0.f);
       float ad = 0.f;
       unsigned mm = members;
       while (mm) {
@@ -1276,15 +1301,15 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : (DUAL ? R3D_BWD_DUAL_BLOCK
         lds_v4(p_top - zc * (4u * S::PROW), p4.x, p4.y, p4.z, p4.w);
 #pragma unroll
         for (int pass = 0; pass < S::PASSES; ++pass) {
-          a[pass].x = fmaf(wm[pass], p4.x, a[pass].x), a[pass].y = fmaf(wm[pass], p4.y, a[pass].y);
-          a[pass].z = fmaf(wm[pass], p4.z, a[pass].z), a[pass].w = fmaf(wm[pass], p4.w, a[pass].w);
+          a01[pass] = ffma2(make_float2(p4.x, p4.y), wm[pass], a01[pass]);
+          a23[pass] = ffma2(make_float2(p4.z, p4.w), wm[pass], a23[pass]);
         }
       }
       const int* VL = sm.V + L * S::WROW;
       if (b.gfeat && role_ok && band_ok) {
 #pragma unroll
         for (int pass = 0; pass < S::PASSES; ++pass) {
-          const float4 v = a[pass];
+          const float4 v = make_float4(a01[pass].x, a01[pass].y, a23[pass].x, a23[pass].y);
           // 32x32 -> 64-bit unsigned multiply: record offsets exceed 2^31 floats at 512^3 / degree 3
           float* dst = b.gfeat + (size_t)(unsigned)VL[pass * S::CPP + cq] * (size_t)ustride + 4 * cj;
           if constexpr (VEC != 0) {
@@ -1399,17 +1424,17 @@ static bool mask_usable(const GridP& g, const BwdP& b, int vec) {
 }
 
 // warp-specialised forward (r3d_fwd_ws.cuh): 4 producer + 4 consumer warps per CTA, dynamic shared memory
-template <int DEG, bool DUAL, bool SORT>
+template <int DEG, bool DUAL, bool SORT, int PF = 0, bool DQ = false>
 static void launch_fwd_ws(dim3 grid, cudaStream_t st, const GridP& g, const RaysP& r, const CfgP& c, const OutP& o) {
   // the per-CTA stratum table needs one (near, far) for all rays and has to fit beside the stage rings
   const bool table = r.bounds == nullptr && !(c.flags & R3D_FLAG_OPTIMIZED_SAMPLING) && c.S <= 4096;
   const size_t smem = ws_smem_bytes<DEG, DUAL>(c.S, table);
   static const bool attr = [] {
-    cudaFuncSetAttribute(render_fwd_ws_kernel<DEG, DUAL, SORT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws_smem_bytes<DEG, DUAL>(4096, true));
+    cudaFuncSetAttribute(render_fwd_ws_kernel<DEG, DUAL, SORT, PF, DQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws_smem_bytes<DEG, DUAL>(4096, true));
     return true;
   }();
   (void)attr;
-  render_fwd_ws_kernel<DEG, DUAL, SORT><<<grid, 256, smem, st>>>(g, r, c, o, table ? 1 : 0);
+  render_fwd_ws_kernel<DEG, DUAL, SORT, PF, DQ><<<grid, 256, smem, st>>>(g, r, c, o, table ? 1 : 0);
 }
 
 template <int DEG>
@@ -1433,10 +1458,20 @@ static void launch_fwd(int vec, int variant, dim3 grid, cudaStream_t st, const G
         return v;
       }();
       (void)carve;
-      if ((variant & 96) == 96)
+      if ((variant & 96) == 96 && (variant & 256) && (variant & 1024))
+        launch_fwd_ws<DEG, false, true, 1, true>(grid, st, g, r, c, o);
+      else if ((variant & 96) == 96 && (variant & 1024))
+        launch_fwd_ws<DEG, false, true, 0, true>(grid, st, g, r, c, o);
+      else if ((variant & 96) == 96 && (variant & 256))
+        launch_fwd_ws<DEG, false, true, 1>(grid, st, g, r, c, o);
+      else if ((variant & 96) == 96 && (variant & 512))
+        launch_fwd_ws<DEG, false, true, 2>(grid, st, g, r, c, o);
+      else if ((variant & 96) == 96)
         launch_fwd_ws<DEG, false, true>(grid, st, g, r, c, o);
       else if (variant & 32)
         launch_fwd_ws<DEG, false, false>(grid, st, g, r, c, o);
+      else if (variant & 2048)
+        render_fwd_group_kernel<DEG, false, true><<<grid, 128, 0, st>>>(g, r, c, o);
       else
         render_fwd_group_kernel<DEG, false><<<grid, 128, 0, st>>>(g, r, c, o);
     }
@@ -1449,6 +1484,19 @@ static void launch_fwd(int vec, int variant, dim3 grid, cudaStream_t st, const G
   else
     render_fwd_kernel<DEG, 0><<<grid, 128, 0, st>>>(g, r, c, o);
 }
+// warp-specialised backward (r3d_bwd_ws.cuh): ReLU field + the forward's sample cache and ballots
+template <int DEG, bool DUAL>
+static void launch_bwd_ws(dim3 grid, cudaStream_t st, const GridP& g, const RaysP& r, const CfgP& c, const BwdP& b) {
+  const bool table = r.bounds == nullptr && !(c.flags & R3D_FLAG_OPTIMIZED_SAMPLING) && c.S <= 4096;
+  const size_t smem = wsb_smem_bytes<DEG, DUAL>(c.S, table);
+  static const bool attr = [] {
+    cudaFuncSetAttribute(render_bwd_ws_kernel<DEG, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsb_smem_bytes<DEG, DUAL>(4096, true));
+    return true;
+  }();
+  (void)attr;
+  render_bwd_ws_kernel<DEG, DUAL><<<grid, 256, smem, st>>>(g, r, c, b, table ? 1 : 0);
+}
+
 template <int DEG>
 static void launch_bwd(int vec, int variant, dim3 grid, cudaStream_t st, const GridP& g, const RaysP& r, const CfgP& c, const BwdP& b) {
   if (variant & 1) {  // thread-per-ray scatter (kept for A/B measurement)
@@ -1461,7 +1509,9 @@ static void launch_bwd(int vec, int variant, dim3 grid, cudaStream_t st, const G
     return;
   }
   if (mask_usable(g, b, vec)) {
-    if (vec == 8)
+    if (variant & 128)
+      launch_bwd_ws<DEG, false>(grid, st, g, r, c, b);
+    else if (vec == 8)
       render_bwd_coop_kernel<DEG, 8, false, true><<<grid, 128, 0, st>>>(g, r, c, b);
     else
       render_bwd_coop_kernel<DEG, 4, false, true><<<grid, 128, 0, st>>>(g, r, c, b);

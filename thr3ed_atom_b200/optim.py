@@ -41,4 +41,5 @@ class FusedGridAdam(torch.optim.Optimizer):
                     p.data, p.grad, state["exp_avg"], state["exp_avg_sq"],
                     lr=float(group["lr"]), beta1=beta1, beta2=beta2, eps=group["eps"], step=state["step"],
                 )
+                torch.autograd.graph.increment_version(p)  # written behind autograd's back: derived buffers must notice
         return loss

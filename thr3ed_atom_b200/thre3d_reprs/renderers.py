@@ -93,6 +93,36 @@ def _current_hints() -> dict:
 _direct_grad_targets = {}
 
 
+def register_direct_grad_target(param: Tensor, buffer: Tensor) -> int:
+    """Make the backward kernel accumulate the gradient of ``param`` straight into ``buffer`` (same shape).  The entry is
+    keyed by the storage address the kernels see and remembers its owner weakly: it is ignored (and dropped) once the
+    parameter is gone or has moved to other storage, so a stale address re-used by the caching allocator can never route
+    another tensor's gradient into an old buffer."""
+    import weakref
+
+    if tuple(buffer.shape) != tuple(param.shape) or buffer.device != param.device:
+        raise ValueError("direct gradient target must match the parameter's shape and device")
+    key = param.data_ptr()
+    _direct_grad_targets[key] = (weakref.ref(param), buffer)
+    return key
+
+
+def unregister_direct_grad_target(key: int) -> None:
+    _direct_grad_targets.pop(key, None)
+
+
+def _lookup_direct_grad_target(storage: Tensor) -> Optional[Tensor]:
+    key = storage.data_ptr()
+    entry = _direct_grad_targets.get(key)
+    if entry is None:
+        return None
+    owner, buffer = entry[0](), entry[1]
+    if owner is None or owner.data_ptr() != key or tuple(owner.shape) != tuple(storage.shape):
+        _direct_grad_targets.pop(key, None)  # the registered parameter died or was re-allocated (.to(), stage upscale)
+        return None
+    return buffer
+
+
 class _FusedSHVoxGridRender(torch.autograd.Function):
     @staticmethod
     def forward(ctx, densities: Tensor, features: Tensor, origins: Tensor, directions: Tensor, grid: VoxelGrid, args: _kernels.RenderArgs,
@@ -130,8 +160,8 @@ class _FusedSHVoxGridRender(torch.autograd.Function):
             (origins, directions, colour, depth, acc), colour_d = ctx.saved_tensors, None
         desc = ctx.desc
         need_d, need_f = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        direct_d = _direct_grad_targets.get(desc.densities.data_ptr()) if need_d else None
-        direct_f = _direct_grad_targets.get(desc.features.data_ptr()) if need_f else None
+        direct_d = _lookup_direct_grad_target(desc.densities) if need_d else None
+        direct_f = _lookup_direct_grad_target(desc.features) if need_f else None
         grad_d = direct_d if direct_d is not None else (torch.zeros_like(desc.densities) if need_d else None)
         grad_f = direct_f if direct_f is not None else (torch.zeros_like(desc.features) if need_f else None)
         if need_d or need_f:
