@@ -153,6 +153,9 @@ typedef struct R3dGridGrad {
 } R3dGridGrad;
 
 R3D_API int r3d_abi_version(void);
+/* 1 when the library was built with -DR3D_AB_VARIANTS (R3dRenderConfig.variant != 0 selects measurement-only kernels),
+ * 0 for the product build, which carries only the kernels the dispatch uses and refuses a non-zero variant. */
+R3D_API int r3d_has_ab_variants(void);
 /* words per sample of R3dRenderOut.sample_mask for this ray batch (= warps of the render launch) */
 R3D_API int64_t r3d_sample_mask_words(const R3dRays* rays);
 R3D_API const char* r3d_last_error(void);

@@ -477,6 +477,10 @@ def test_cooperative_and_per_ray_kernels_agree(name, cuda_device, monkeypatch):
     Gradients are equal up to summation order."""
     from thr3ed_atom_b200.thre3d_reprs.renderers import render_hints, render_sh_voxel_grid
 
+    from thr3ed_atom_b200 import _kernels
+
+    if not _kernels.has_ab_variants():
+        pytest.skip("product build: A/B kernel variants are compiled only with -DR3D_AB_VARIANTS (python -m thr3ed_atom_b200.build --ab)")
     case = CASES[name]
     inp = build_inputs(case)
     gc = torch.from_numpy(inp["grad_colour"]).to(cuda_device)
@@ -596,10 +600,14 @@ def test_sample_mask_is_refused_when_another_forward_kernel_would_run(cuda_devic
     mask = _kernels.new_sample_mask(desc, o, d, o.shape[0], args)
     assert mask.shape == (args.num_samples, (o.shape[0] + 127) // 128 * 4)
     _kernels.render_forward(desc, o, d, args, cache, sample_mask=mask)  # default kernel: accepted
-    args.variant = 8
-    with pytest.raises(RuntimeError, match="sample_mask needs"):
+    args.variant = 8  # staged forward (A/B builds), refused outright by the product build
+    with pytest.raises(RuntimeError, match="sample_mask needs|A/B variants are compiled only"):
         _kernels.render_forward(desc, o, d, args, cache, sample_mask=mask)
     args.variant = 0
+    args.diffuse = True  # band-0-only renders use the per-ray kernel, which writes no ballots
+    with pytest.raises(RuntimeError, match="sample_mask needs"):
+        _kernels.render_forward(desc, o, d, args, cache, sample_mask=mask)
+    args.diffuse = False
     with pytest.raises(RuntimeError, match="sample_mask needs"):
         _kernels.render_forward(desc, o, d, args, None, sample_mask=mask)
 

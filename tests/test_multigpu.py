@@ -109,19 +109,44 @@ def _sharded_adam_worker(rank, world, port, tmp):
             assert torch.equal(p.detach(), b)  # re-homing keeps the values
         assert opt_b.state["exp_avg"].numel() * world >= opt_b.total  # 1/n of the optimizer state per GPU
         assert opt_b.state["exp_avg"].numel() <= opt_b.total // world + 4
-        for step in range(3):
+        inits = [p.detach().clone() for p in grid_b.parameters()]
+
+        def one_step(backward_a, backward_b):
             opt_a.zero_grad()
-            local_backward(grid_a)
+            backward_a()
             all_reduce_grid_gradients(grid_a)
             opt_a.step()
             opt_b.zero_grad()
-            local_backward(grid_b)
+            backward_b()
             opt_b.step()
             torch.cuda.synchronize()
-            for pa, pb in zip(grid_a.parameters(), grid_b.parameters()):
-                # Adam's first steps move every touched element by ~lr: compare the updates, not only the values
-                err = float((pa.detach() - pb.detach()).abs().max())
-                assert err < 2e-4 * lr + 1e-6, (step, err)
+
+        # (1) exact phase: only rank 0 renders, rank 1 contributes zeros, so both paths see the SAME summed gradient bits
+        #     (x + 0 = x) and the fused kernel must reproduce torch.optim.Adam's arithmetic, not just its statistics
+        full = shard_rays(rays, gc, rank=0, world_size=1)
+
+        def all_rays(grid):
+            if rank == 0:
+                out = render_sh_voxel_grid(grid, full.rays, make_cuda_config(case))
+                (out.colour * full.pixels).sum().backward()
+            else:
+                for p in grid.parameters():
+                    if p.grad is None:
+                        p.grad = torch.zeros_like(p)
+
+        one_step(lambda: all_rays(grid_a), lambda: all_rays(grid_b))
+        for pa, pb, p0 in zip(grid_a.parameters(), grid_b.parameters(), inits):
+            assert float((pb.detach() - p0).abs().max()) > 0.5 * lr  # the step did move the parameters
+            assert float((pa.detach() - pb.detach()).abs().max()) < 1e-6, "fused Adam arithmetic differs from torch.optim.Adam"
+        # (2) sharded rays, two more steps: the summation order inside the switch differs from NCCL's, and Adam amplifies a
+        #     rounding-level difference wherever |g| ~ eps (sum of the ranks' parts cancels), so the comparison is statistical
+        for step in range(2):
+            one_step(lambda: local_backward(grid_a), lambda: local_backward(grid_b))
+            for pa, pb, p0 in zip(grid_a.parameters(), grid_b.parameters(), inits):
+                ua, ub = (pa.detach() - p0).double(), (pb.detach() - p0).double()
+                rel = float((ua - ub).norm() / ua.norm())
+                outliers = float(((ua - ub).abs() > 1e-3 * lr).double().mean())
+                assert rel < 5e-3 and outliers < 1e-3, (step, rel, outliers)
         # the replicas stay identical across ranks (every rank received every slice)
         for pb in grid_b.parameters():
             mine = pb.detach().clone()

@@ -92,6 +92,7 @@ class R3dGridGrad(C.Structure):
 # name -> (restype, argtypes); every symbol include/r3d_b200.h declares
 SIGNATURES = {
     "r3d_abi_version": (C.c_int, []),
+    "r3d_has_ab_variants": (C.c_int, []),
     "r3d_last_error": (C.c_char_p, []),
     "r3d_sample_mask_words": (C.c_int64, [C.POINTER(R3dRays)]),
     "r3d_render_fwd": (C.c_int, [C.POINTER(R3dGrid), C.POINTER(R3dRays), C.POINTER(R3dRenderConfig), C.POINTER(R3dRenderOut), C.c_void_p]),

@@ -195,7 +195,9 @@ def sample_mask_supported(grid: GridDesc, args: RenderArgs) -> bool:
     the backward use them (ReLU density post-activation)?  Mirrors ``fwd_uses_group_kernel`` / ``mask_usable`` in
     ``csrc/r3d_render.cu``; the library refuses a mask it would not write."""
     f = grid.features
-    return ((args.variant & ~(96 | 128 | 256 | 512 | 1024 | 2048)) == 0 and not args.diffuse and grid.density_post == _abi.POST_RELU and f.shape[3] % 4 == 0
+    # A/B builds only: the warp-specialised / cell-sorted forward variants write the ballots too, the per-ray and staged ones
+    # (bits 2, 4, 8) do not; bit 1 and 128 select backward kernels
+    return ((args.variant & (2 | 4 | 8)) == 0 and not args.diffuse and grid.density_post == _abi.POST_RELU and f.shape[3] % 4 == 0
             and f.data_ptr() % 16 == 0 and f.shape[0] * f.shape[1] * f.shape[2] * (f.shape[3] // 4) <= 0xFFFFFFFF)
 
 
@@ -387,3 +389,8 @@ def multimem_adam_step(grad_multicast_ptr: int, param_multicast_ptr: int, param_
             ),
             "r3d_multimem_adam_step",
         )
+
+
+def has_ab_variants() -> bool:
+    """Was the loaded library built with -DR3D_AB_VARIANTS (measurement-only kernel variants selectable)?"""
+    return bool(_abi.lib().r3d_has_ab_variants())

@@ -55,6 +55,25 @@ def is_current() -> bool:
     return LIB_PATH.exists() and STAMP.exists() and STAMP.read_text().strip() == _source_digest()
 
 
+AB_LIB_PATH = LIB_DIR / "libr3d_b200_ab.so"
+
+
+def build_ab(verbose: bool = False) -> Path:
+    """Measurement build with every A/B kernel variant (-DR3D_AB_VARIANTS): ``R3D_LIB_PATH=<this file>`` selects it.  The
+    product library (``build()``) carries only the kernels its dispatch uses and refuses ``R3dRenderConfig.variant != 0``."""
+    LIB_DIR.mkdir(exist_ok=True)
+    cmd = [_nvcc(), *NVCC_FLAGS, "-DR3D_AB_VARIANTS", *_extra_flags(), f"-I{INCLUDE}", f"-I{CSRC}", "-o", str(AB_LIB_PATH)]
+    if verbose:
+        cmd += ["-Xptxas", "-v"]
+    cmd += [str(CSRC / s) for s in SOURCES]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError(f"nvcc failed ({proc.returncode}):\n{' '.join(cmd)}\n{proc.stdout}\n{proc.stderr}")
+    if verbose:
+        sys.stderr.write(proc.stderr)
+    return AB_LIB_PATH
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
     """Compile the library if the sources changed since the last build; returns its path."""
     if not force and is_current():
@@ -74,5 +93,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
 
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
-    print(path)
+    if "--ab" in sys.argv:
+        print(build_ab(verbose="-v" in sys.argv))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

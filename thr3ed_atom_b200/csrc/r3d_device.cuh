@@ -476,4 +476,24 @@ __device__ __forceinline__ float sigmoidf_(float x) {
 #endif
 }
 
+// Packed fp32 FMA (new on sm_100: SASS FFMA2 Rd, Ra.F32x2, Rb.F32 (broadcast), Rc.F32x2): a.xy * b + c.xy in ONE issue slot.
+// Measured on the B200 (profiles/r02_ubench_ffma2.json): the FMA rate stays 128 lanes/clk/SM, the issue slots halve.
+#ifndef R3D_FFMA2
+#define R3D_FFMA2 1
+#endif
+__device__ __forceinline__ float2 ffma2(const float2 a, const float b, const float2 c) {
+#if R3D_FFMA2
+  // packed fp32 FMA (sm_100: FFMA2 Rd, Ra.F32x2, Rb.F32 (broadcast), Rc.F32x2): two FMAs per issue slot
+  const float2 bb = make_float2(b, b);
+  unsigned long long rd;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(rd)
+      : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&bb)),
+        "l"(*reinterpret_cast<const unsigned long long*>(&c)));
+  return *reinterpret_cast<float2*>(&rd);
+#else
+  return make_float2(fmaf(a.x, b, c.x), fmaf(a.y, b, c.y));
+#endif
+}
+
 }  // namespace r3d

@@ -34,9 +34,6 @@
 #ifndef R3D_WS_LAG
 #define R3D_WS_LAG 3
 #endif
-#ifndef R3D_WS_FFMA2
-#define R3D_WS_FFMA2 1
-#endif
 
 namespace r3d {
 
@@ -77,21 +74,6 @@ __device__ __forceinline__ bool mbar_test(unsigned long long* bar, unsigned pari
 
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
-}
-
-__device__ __forceinline__ float2 ffma2(const float2 a, const float b, const float2 c) {
-#if R3D_WS_FFMA2
-  // packed fp32 FMA (sm_100: FFMA2 Rd, Ra.F32x2, Rb.F32 (broadcast), Rc.F32x2): two FMAs per issue slot
-  const float2 bb = make_float2(b, b);
-  unsigned long long rd;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;"
-      : "=l"(rd)
-      : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&bb)),
-        "l"(*reinterpret_cast<const unsigned long long*>(&c)));
-  return *reinterpret_cast<float2*>(&rd);
-#else
-  return make_float2(fmaf(a.x, b, c.x), fmaf(a.y, b, c.y));
-#endif
 }
 
 template <bool DUAL>

@@ -322,6 +322,7 @@ __global__ void __launch_bounds__(128) render_fwd_kernel(const GridP g, const Ra
 }
 
 
+#ifdef R3D_AB_VARIANTS  // staged forward variants (cp.async / TMA bulk copies through shared memory): measurement only
 // =================================================================================================
 // forward, warp-cooperative gather (default for the padded layouts, non-diffuse)
 //
@@ -563,6 +564,8 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_FWD_BLOCKS) render_fwd
     out.disparity[ray] = __fdiv_rn(1.0f, m);
   }
 }
+
+#endif  // R3D_AB_VARIANTS
 
 // =================================================================================================
 // forward, lane-group gather (default for the padded layouts, non-diffuse)
@@ -867,9 +870,11 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_FWD_BLOCKS) render_fwd
   }
 }
 
+#ifdef R3D_AB_VARIANTS
 }  // namespace r3d
 #include "r3d_fwd_ws.cuh"
 namespace r3d {
+#endif
 
 // Per-ray upstream gradients folded into the three numbers the march needs: g_c (3), g_d, g_a, plus
 // Total = sum_i w_i q_i rebuilt from the forward outputs.  Returns false when the ray receives no gradient.
@@ -920,10 +925,13 @@ __device__ __forceinline__ bool load_ray_grad(const BwdP& b, const CfgP& c, long
   return !(gc[0] == 0.f && gc[1] == 0.f && gc[2] == 0.f && gd == 0.f && ga == 0.f && gcd[0] == 0.f && gcd[1] == 0.f && gcd[2] == 0.f);
 }
 
+#ifdef R3D_AB_VARIANTS
 }  // namespace r3d
 #include "r3d_bwd_ws.cuh"
 namespace r3d {
+#endif
 
+#ifdef R3D_AB_VARIANTS  // thread-per-ray backward: measurement only
 // =================================================================================================
 // backward
 // =================================================================================================
@@ -1025,6 +1033,8 @@ __global__ void __launch_bounds__(128) render_bwd_kernel(const GridP g, const Ra
   }
 }
 
+
+#endif  // R3D_AB_VARIANTS
 
 // =================================================================================================
 // backward, warp-cooperative scatter (default)
@@ -1415,7 +1425,7 @@ static bool group_indexable(const GridP& g) {
 // does r3d_render_fwd dispatch the lane-group kernel (the one that writes OutP::mask) for these arguments?
 static bool fwd_uses_group_kernel(const GridP& g, const CfgP& c, int vec, int variant, int sh_degree) {
   const bool diffuse = (c.flags & R3D_FLAG_DIFFUSE) != 0 && sh_degree > 0;
-  return vec != 0 && !diffuse && !(variant & (2 | 4 | 8)) && group_indexable(g);
+  return vec != 0 && !diffuse && !(variant & (2 | 4 | 8)) && group_indexable(g);  // (the ws / sorted variants write it too)
 }
 // the backward can march by the forward's contribution ballots when it also has the per-sample records (sigma) and the
 // density post-activation is ReLU (see render_bwd_coop_kernel)
@@ -1424,6 +1434,7 @@ static bool mask_usable(const GridP& g, const BwdP& b, int vec) {
 }
 
 // warp-specialised forward (r3d_fwd_ws.cuh): 4 producer + 4 consumer warps per CTA, dynamic shared memory
+#ifdef R3D_AB_VARIANTS
 template <int DEG, bool DUAL, bool SORT, int PF = 0, bool DQ = false>
 static void launch_fwd_ws(dim3 grid, cudaStream_t st, const GridP& g, const RaysP& r, const CfgP& c, const OutP& o) {
   // the per-CTA stratum table needs one (near, far) for all rays and has to fit beside the stage rings
@@ -1437,27 +1448,24 @@ static void launch_fwd_ws(dim3 grid, cudaStream_t st, const GridP& g, const Rays
   render_fwd_ws_kernel<DEG, DUAL, SORT, PF, DQ><<<grid, 256, smem, st>>>(g, r, c, o, table ? 1 : 0);
 }
 
+#endif
+
 template <int DEG>
 static void launch_fwd(int vec, int variant, dim3 grid, cudaStream_t st, const GridP& g, const RaysP& r, const CfgP& c, const OutP& o) {
-  // cooperative gather needs 16-byte aligned records; band-0-only (diffuse) renders read 3 floats per record and
-  // keep the per-ray gather
+  // the lane-group gather needs 16-byte aligned records addressable with 32-bit float4 indices; band-0-only (diffuse) renders
+  // read 3 floats per record and keep the per-ray gather
   const bool diffuse = (c.flags & R3D_FLAG_DIFFUSE) != 0 && DEG > 0;
+#ifdef R3D_AB_VARIANTS
   if (vec != 0 && !diffuse && !(variant & 2)) {
-    if (variant & 4)  // TMA (cp.async.bulk) staging instead of per-lane cp.async: measured, see DESIGN.md
+    if (variant & 4) {  // TMA (cp.async.bulk) staging instead of per-lane cp.async: measured, see DESIGN.md
       render_fwd_coop_kernel<DEG, true><<<grid, 128, 0, st>>>(g, r, c, o);
-    else if ((variant & 8) || !group_indexable(g))
-      // shared-memory staged gather (the default before the lane-group kernel, which addresses records with 32-bit
-      // float4 indices; no supported grid exceeds them: 512^3 at degree 3 is 1.6 G)
+      return;
+    }
+    if (variant & 8) {  // shared-memory staged gather (the default before the lane-group kernel)
       render_fwd_coop_kernel<DEG, false><<<grid, 128, 0, st>>>(g, r, c, o);
-    else {
-      // tuning hook: $R3D_FWD_CARVEOUT = preferred shared-memory carve-out in percent (the rest of the 228 KB is L1)
-      static const int carve = [] {
-        const char* e = getenv("R3D_FWD_CARVEOUT");
-        const int v = e ? atoi(e) : -1;
-        if (v >= 0) cudaFuncSetAttribute(render_fwd_group_kernel<DEG, false>, cudaFuncAttributePreferredSharedMemoryCarveout, v);
-        return v;
-      }();
-      (void)carve;
+      return;
+    }
+    if (group_indexable(g) && (variant & (32 | 2048))) {
       if ((variant & 96) == 96 && (variant & 256) && (variant & 1024))
         launch_fwd_ws<DEG, false, true, 1, true>(grid, st, g, r, c, o);
       else if ((variant & 96) == 96 && (variant & 1024))
@@ -1470,20 +1478,41 @@ static void launch_fwd(int vec, int variant, dim3 grid, cudaStream_t st, const G
         launch_fwd_ws<DEG, false, true>(grid, st, g, r, c, o);
       else if (variant & 32)
         launch_fwd_ws<DEG, false, false>(grid, st, g, r, c, o);
-      else if (variant & 2048)
-        render_fwd_group_kernel<DEG, false, true><<<grid, 128, 0, st>>>(g, r, c, o);
       else
-        render_fwd_group_kernel<DEG, false><<<grid, 128, 0, st>>>(g, r, c, o);
+        render_fwd_group_kernel<DEG, false, true><<<grid, 128, 0, st>>>(g, r, c, o);
+      return;
     }
+  }
+  const bool per_ray = (variant & 2) != 0;
+#else
+  (void)variant;
+  const bool per_ray = false;
+#endif
+  if (vec != 0 && !diffuse && !per_ray && group_indexable(g)) {
+    // tuning hook: $R3D_FWD_CARVEOUT = preferred shared-memory carve-out in percent (the rest of the 228 KB is L1)
+    static const int carve = [] {
+      const char* e = getenv("R3D_FWD_CARVEOUT");
+      const int v = e ? atoi(e) : -1;
+      if (v >= 0) cudaFuncSetAttribute(render_fwd_group_kernel<DEG, false>, cudaFuncAttributePreferredSharedMemoryCarveout, v);
+      return v;
+    }();
+    (void)carve;
+    render_fwd_group_kernel<DEG, false><<<grid, 128, 0, st>>>(g, r, c, o);
     return;
   }
-  if (vec == 8)
+#ifdef R3D_AB_VARIANTS
+  if (vec == 8) {  // 256-bit record loads (R3D_FEATURE_PAD=8 layouts): measured, no gain
     render_fwd_kernel<DEG, 8><<<grid, 128, 0, st>>>(g, r, c, o);
-  else if (vec == 4)
+    return;
+  }
+#endif
+  if (vec != 0)
     render_fwd_kernel<DEG, 4><<<grid, 128, 0, st>>>(g, r, c, o);
   else
     render_fwd_kernel<DEG, 0><<<grid, 128, 0, st>>>(g, r, c, o);
 }
+
+#ifdef R3D_AB_VARIANTS
 // warp-specialised backward (r3d_bwd_ws.cuh): ReLU field + the forward's sample cache and ballots
 template <int DEG, bool DUAL>
 static void launch_bwd_ws(dim3 grid, cudaStream_t st, const GridP& g, const RaysP& r, const CfgP& c, const BwdP& b) {
@@ -1497,8 +1526,11 @@ static void launch_bwd_ws(dim3 grid, cudaStream_t st, const GridP& g, const Rays
   render_bwd_ws_kernel<DEG, DUAL><<<grid, 256, smem, st>>>(g, r, c, b, table ? 1 : 0);
 }
 
+#endif
+
 template <int DEG>
 static void launch_bwd(int vec, int variant, dim3 grid, cudaStream_t st, const GridP& g, const RaysP& r, const CfgP& c, const BwdP& b) {
+#ifdef R3D_AB_VARIANTS
   if (variant & 1) {  // thread-per-ray scatter (kept for A/B measurement)
     if (vec == 8)
       render_bwd_kernel<DEG, 8><<<grid, 128, 0, st>>>(g, r, c, b);
@@ -1508,18 +1540,17 @@ static void launch_bwd(int vec, int variant, dim3 grid, cudaStream_t st, const G
       render_bwd_kernel<DEG, 0><<<grid, 128, 0, st>>>(g, r, c, b);
     return;
   }
-  if (mask_usable(g, b, vec)) {
-    if (variant & 128)
-      launch_bwd_ws<DEG, false>(grid, st, g, r, c, b);
-    else if (vec == 8)
-      render_bwd_coop_kernel<DEG, 8, false, true><<<grid, 128, 0, st>>>(g, r, c, b);
-    else
-      render_bwd_coop_kernel<DEG, 4, false, true><<<grid, 128, 0, st>>>(g, r, c, b);
+  if (mask_usable(g, b, vec) && (variant & 128)) {
+    launch_bwd_ws<DEG, false>(grid, st, g, r, c, b);
     return;
   }
-  if (vec == 8)
-    render_bwd_coop_kernel<DEG, 8, false, false><<<grid, 128, 0, st>>>(g, r, c, b);
-  else if (vec == 4)
+#else
+  (void)variant;
+#endif
+  // 128-bit vector reductions whenever the layout allows (a stride that is a multiple of 8 floats is one of 4 too)
+  if (mask_usable(g, b, vec))
+    render_bwd_coop_kernel<DEG, 4, false, true><<<grid, 128, 0, st>>>(g, r, c, b);
+  else if (vec != 0)
     render_bwd_coop_kernel<DEG, 4, false, false><<<grid, 128, 0, st>>>(g, r, c, b);
   else
     render_bwd_coop_kernel<DEG, 0, false, false><<<grid, 128, 0, st>>>(g, r, c, b);
@@ -1535,15 +1566,8 @@ static void launch_fwd_dual(dim3 grid, cudaStream_t st, const GridP& g, const Ra
 }
 template <int DEG>
 static void launch_bwd_dual(int vec, dim3 grid, cudaStream_t st, const GridP& g, const RaysP& r, const CfgP& c, const BwdP& b) {
-  if (mask_usable(g, b, vec)) {
-    if (vec == 8)
-      render_bwd_coop_kernel<DEG, 8, true, true><<<grid, 128, 0, st>>>(g, r, c, b);
-    else
-      render_bwd_coop_kernel<DEG, 4, true, true><<<grid, 128, 0, st>>>(g, r, c, b);
-    return;
-  }
-  if (vec == 8)
-    render_bwd_coop_kernel<DEG, 8, true, false><<<grid, 128, 0, st>>>(g, r, c, b);
+  if (mask_usable(g, b, vec))
+    render_bwd_coop_kernel<DEG, 4, true, true><<<grid, 128, 0, st>>>(g, r, c, b);
   else
     render_bwd_coop_kernel<DEG, 4, true, false><<<grid, 128, 0, st>>>(g, r, c, b);
 }
@@ -1589,6 +1613,9 @@ extern "C" int r3d_render_fwd(const R3dGrid* grid, const R3dRays* rays, const R3
          out->colour_diffuse, reinterpret_cast<float4*>(out->sample_cache_diffuse), out->sample_mask};
   if ((o.cache && !aligned16(o.cache)) || (o.cache_diffuse && !aligned16(o.cache_diffuse)))
     return fail(R3D_ERR_INVALID_ARGUMENT, "sample_cache must be 16-byte aligned");
+#ifndef R3D_AB_VARIANTS
+  if (cfg->variant != 0) return fail(R3D_ERR_UNSUPPORTED, "kernel variant %d: A/B variants are compiled only with -DR3D_AB_VARIANTS", cfg->variant);
+#endif
   dim3 blocks;
   if ((rc = grid_blocks(r, blocks))) return rc;
   const int vec = vector_width(g, nullptr);
@@ -1637,6 +1664,9 @@ extern "C" int r3d_render_bwd(const R3dGrid* grid, const R3dRays* rays, const R3
          saved->sample_mask};
   if ((b.cache && !aligned16(b.cache)) || (b.cache_diffuse && !aligned16(b.cache_diffuse)))
     return fail(R3D_ERR_INVALID_ARGUMENT, "sample_cache must be 16-byte aligned");
+#ifndef R3D_AB_VARIANTS
+  if (cfg->variant != 0) return fail(R3D_ERR_UNSUPPORTED, "kernel variant %d: A/B variants are compiled only with -DR3D_AB_VARIANTS", cfg->variant);
+#endif
   dim3 blocks;
   if ((rc = grid_blocks(r, blocks))) return rc;
   const int vec = vector_width(g, b.gfeat);
@@ -1692,4 +1722,12 @@ extern "C" int r3d_sample_statistics(const R3dGrid* grid, const R3dRays* rays, c
   if ((rc = grid_blocks(r, blocks))) return rc;
   sample_stats_kernel<<<blocks, 128, 0, static_cast<cudaStream_t>(cuda_stream)>>>(g, r, c, reinterpret_cast<unsigned long long*>(counters));
   return check_launch("r3d_sample_statistics");
+}
+
+extern "C" int r3d_has_ab_variants(void) {
+#ifdef R3D_AB_VARIANTS
+  return 1;
+#else
+  return 0;
+#endif
 }
