@@ -323,6 +323,9 @@ def main():
     ap.add_argument("--no-perturb", action="store_true")
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--flat-order", action="store_true", help="do not pass the image-shape hint (rays in list order)")
+    ap.add_argument("--strong", action="store_true",
+                    help="strong scaling (BASELINE.json configs[3] read literally): ONE 800x800 view, its rays sharded over the ranks in "
+                         "contiguous row blocks (distributed.shard_rays); default is weak scaling, one full view per rank")
     ap.add_argument("--no-optimizer", action="store_true",
                     help="round-1 step definition: forward + backward (+ gradient all-reduce at N > 1), no optimizer step")
     ap.add_argument("--lr", type=float, default=1e-5,
@@ -383,15 +386,24 @@ def main():
                                 perturb_sampled_points=not args.no_perturb, white_bkgd=True)
     vol_mod = VolumetricModel(voxel_grid, render_sh_voxel_grid, cfg, device=device)
 
-    rot, trans, focal = camera_for_rank(rank, side)
+    rot, trans, focal = camera_for_rank(0 if args.strong else rank, side)
     rays = flatten_rays(cast_rays(CameraIntrinsics(side, side, focal), CameraPose(rot, trans), device=device))
+    gen = torch.Generator().manual_seed(7 + (0 if args.strong else rank))
+    pixels_host = torch.rand((len(rays), 3), generator=gen)
+    rows = side
+    if args.strong and world > 1:
+        from thr3ed_atom_b200.distributed import shard_rays
+
+        assert side % world == 0, "--strong shards whole image rows"
+        shard = shard_rays(rays, pixels_host)  # contiguous block of rows: the image-tile mapping stays valid inside a rank
+        rays = Rays(shard.rays.origins.contiguous(), shard.rays.directions.contiguous())
+        pixels_host, rows = shard.pixels.contiguous(), side // world
     n_rays = len(rays)
-    gen = torch.Generator().manual_seed(7 + rank)
-    pixels_host = torch.rand((n_rays, 3), generator=gen).pin_memory()
+    pixels_host = pixels_host.pin_memory()
     pixels = pixels_host.to(device)
     origins_host, dirs_host = rays.origins.cpu().pin_memory(), rays.directions.cpu().pin_memory()
     colour_host = torch.empty((n_rays, 3), dtype=torch.float32).pin_memory()
-    hint = None if args.flat_order else (side, side)
+    hint = None if args.flat_order else (rows, side)
 
     # ---- algorithmic bytes + companion figures: exact counts from untimed passes over the same rays ----
     with render_hints(image_hw=hint, rng_seed=1234):
@@ -508,6 +520,8 @@ def main():
         with render_hints(image_hw=hint, variant=args.variant):
             out = vol_mod.render_rays(Rays(o, d))
         loss = torch.nn.functional.l1_loss(out.colour, px)
+        if args.strong and world > 1:
+            loss = loss / world  # equal shards: the sum over ranks of (local mean / world) is the mean over the whole batch
         loss.backward()  # with a direct target the backward kernel accumulates straight into the symmetric buffers
         exchange_and_update()
         return loss, out
@@ -548,10 +562,11 @@ def main():
                       "probe_elements": int(idx.numel()), "max_err_ulps_of_param": err_ulps, "max_err_over_lr": err, "replicas_identical": replicas_equal,
                       "fraction_of_probe_updated": moved, "ok": bool(err_ulps <= 2.0 and replicas_equal and moved > 0.1)}
         else:
-            for p in params:
-                p.grad = None
             if reducer is not None:
                 reducer.zero_grad()
+            else:
+                for p in params:
+                    p.grad = None
             with render_hints(image_hw=hint, variant=args.variant):
                 out = vol_mod.render_rays(rays)
             torch.nn.functional.l1_loss(out.colour, pixels).backward()
@@ -647,7 +662,7 @@ def main():
         clock_summary = clocks.summary()
         sm_mhz = clock_summary.get("sm_mhz") or sm_max
         ms_per_step = total_ms / args.steps
-        value = world * n_rays / (ms_per_step * 1e-3)
+        value = world * n_rays / (ms_per_step * 1e-3)  # weak: n_rays per rank; strong: n_rays is the rank's shard of one view
         opt_name = ("none" if args.no_optimizer else
                     ("in-switch reduce-scatter -> shard-local Adam -> all-gather (r3d_multimem_adam_step)" if sharded is not None else
                      (f"{exchange} all-reduce(grid grad) + " if world > 1 else "") + "fused dense Adam (r3d_adam_step)"))
@@ -658,7 +673,7 @@ def main():
             step_desc += " + optimizer.step: " + opt_name
         line = {
             "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {
                 "workload": args.workload, "grid": grid_n, "sh_degree": deg, "image": [side, side], "samples_per_ray": spp,

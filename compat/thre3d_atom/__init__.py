@@ -120,9 +120,25 @@ class _ReferenceFinder(importlib.abc.MetaPathFinder):
         return importlib.util.spec_from_file_location(fullname, file, submodule_search_locations=[str(file.parent)] if is_pkg else None)
 
 
+def _adopt_reference_names(target: types.ModuleType, shim_name: str) -> None:
+    """Classes and functions DEFINED in a mapped module report the reference's module path while the shim is active, so that
+    what ``VolumetricModel.get_save_info`` pickles by qualified name (``render_sh_voxel_grid``, ``SHVoxGridRenderConfig``,
+    ``density2occupancy_pb``, the camera / voxel NamedTuples; reference modules/volumetric_model.py:83-97) is written under
+    ``thre3d_atom.*`` -- checkpoints saved through the shim stay loadable by the upstream framework."""
+    for attr, obj in list(vars(target).items()):
+        if attr.startswith("_") or not (isinstance(obj, type) or isinstance(obj, types.FunctionType)):
+            continue
+        if getattr(obj, "__module__", None) == target.__name__:
+            try:
+                obj.__module__ = shim_name
+            except (AttributeError, TypeError):
+                pass
+
+
 _ensure_standins()
 for _name in _MAPPED:
     _target = importlib.import_module(f"thr3ed_atom_b200.{_name}")
+    _adopt_reference_names(_target, f"{_PKG}.{_name}")
     sys.modules[f"{_PKG}.{_name}"] = _MappedModule(f"{_PKG}.{_name}", _target, _name) if _REF_ROOT is not None else _target
 for _top in ("utils", "rendering", "thre3d_reprs", "modules"):
     setattr(sys.modules[_PKG], _top, sys.modules[f"{_PKG}.{_top}"])

@@ -179,6 +179,25 @@ R3D_API int r3d_render_bwd(const R3dGrid* grid, const R3dRays* rays, const R3dRe
 /* cast_rays (rendering/volumetric/utils/misc.py:12-50): fills origins/directions [H*W][3]. */
 R3D_API int r3d_cast_rays(const R3dCamera* camera, float* origins, float* directions, void* cuda_stream);
 
+/* A set of posed pinhole views sharing one intrinsics (what the reference trainer keeps cached on the device,
+ * modules/trainers.py:59, data/datasets.py:74-89). */
+typedef struct R3dViewSet {
+  const float* rotations;     /* [V][9] row-major camera-to-world rotations (device) */
+  const float* translations;  /* [V][3] (device) */
+  const float* images;        /* optional [V][H][W][3] target pixels (device, channel-last) */
+  int32_t num_views, height, width;
+  float focal;
+} R3dViewSet;
+
+/* Training-batch sampler: `batch` rays (+ their target pixels) drawn uniformly with replacement from all pixels of all
+ * views, in units of tile_width x tile_height pixel tiles (1 x 1 = independent pixels; 8 x 4 = one coherent tile per warp of
+ * the render kernels).  Replaces cast_rays on every cached view + randperm over all pixels + gathers, every iteration
+ * (modules/trainers.py:281-303, rendering/volumetric/utils/misc.py:117-129).  Rays are bit-identical to r3d_cast_rays for
+ * the same pixel.  Outputs: origins / directions [batch][3], pixels [batch][3] (optional), indices [batch] = flat pixel
+ * index (view*H + y)*W + x (optional).  Counter-based RNG keyed by `seed`: the same seed gives the same batch. */
+R3D_API int r3d_sample_ray_batch(const R3dViewSet* views, int64_t batch, int32_t tile_width, int32_t tile_height, uint64_t seed,
+                                 float* origins, float* directions, float* pixels, int64_t* indices, void* cuda_stream);
+
 /* VoxelGrid.forward (voxels.py:276-331) on free points: out [P][F+1] = (features..., density);
  * `inside` (optional, [P] bytes) = test_inside_volume (voxels.py:252-274). */
 R3D_API int r3d_grid_lookup_fwd(const R3dGrid* grid, const float* points, int64_t num_points, float* out,

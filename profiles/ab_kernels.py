@@ -33,6 +33,7 @@ def main():
     ap.add_argument("--variants", default="0,8")
     ap.add_argument("--pads", default="4")
     ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--grid", type=int, default=256)
     ap.add_argument("--deg", type=int, default=2)
     ap.add_argument("--side", type=int, default=800)
@@ -84,7 +85,7 @@ def main():
                 loss.backward()
                 return o
 
-            for _ in range(3):
+            for _ in range(args.warmup):
                 o = step()
             torch.cuda.synchronize()
             ev["fwd"].clear(), ev["bwd"].clear()

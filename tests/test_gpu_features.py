@@ -641,3 +641,50 @@ def test_no_grad_render_allocates_no_sample_cache(cuda_device, monkeypatch):
     loud = render_sh_voxel_grid(grid, _rays(inp, cuda_device), make_cuda_config(case))
     assert calls["cache"] == 1
     assert torch.equal(quiet.colour, loud.colour.detach())
+
+
+@pytest.mark.parametrize("tile", [(1, 1), (8, 4)])
+def test_device_side_training_batch_sampler(tile, cuda_device):
+    """one kernel replaces cast_rays on every view + randperm + gathers (reference trainers.py:281-303,
+    utils/misc.py:117-129).  Every sampled ray / pixel equals cast_rays / the image at the pixel it names; pixels come in whole
+    tiles; the draw is uniform over views and pixels and reproducible from the seed."""
+    from cases import spherical_pose
+    from thr3ed_atom_b200 import _kernels
+    from thr3ed_atom_b200.rendering.volumetric.utils.misc import cast_rays, flatten_rays, sample_training_ray_batch
+    from thr3ed_atom_b200.utils.imaging_utils import CameraIntrinsics, CameraPose
+
+    v, h, w, focal = 5, 48, 64, 70.0
+    poses = [CameraPose(*spherical_pose(37.0 * k, 30.0 + 7.0 * k, 4.0)) for k in range(v)]
+    gen = torch.Generator().manual_seed(3)
+    images = torch.rand((v, h, w, 3), generator=gen).to(cuda_device)
+    intr = CameraIntrinsics(h, w, focal)
+    batch = 8192
+    rot = torch.stack([torch.as_tensor(p.rotation, dtype=torch.float32).reshape(3, 3) for p in poses]).to(cuda_device)
+    tr = torch.stack([torch.as_tensor(p.translation, dtype=torch.float32).reshape(3) for p in poses]).to(cuda_device)
+    o, d, px, idx = _kernels.sample_ray_batch(rot, tr, images, h, w, focal, batch, tile=tile, seed=99, want_indices=True)
+    assert int(idx.min()) >= 0 and int(idx.max()) < v * h * w
+    all_rays = [flatten_rays(cast_rays(intr, p, device=cuda_device)) for p in poses]
+    ref_o = torch.cat([r.origins for r in all_rays])[idx]
+    ref_d = torch.cat([r.directions for r in all_rays])[idx]
+    assert torch.equal(o, ref_o) and torch.equal(d, ref_d)
+    assert torch.equal(px, images.reshape(-1, 3)[idx])
+    # whole tiles, row-major inside a tile, aligned to the tile grid
+    x, y, view = idx % w, (idx // w) % h, idx // (h * w)
+    tw, th = tile
+    xs, ys, vs = x.reshape(-1, th, tw), y.reshape(-1, th, tw), view.reshape(-1, th, tw)
+    assert bool((xs[:, :, :1] % tw == 0).all()) and bool((ys[:, :1, :] % th == 0).all())
+    assert bool((xs == xs[:, :1, :1] + torch.arange(tw, device=cuda_device)[None, None, :]).all())
+    assert bool((ys == ys[:, :1, :1] + torch.arange(th, device=cuda_device)[None, :, None]).all())
+    assert bool((vs == vs[:, :1, :1]).all())
+    # uniform over views and over the image (loose bounds: 8192 / (tw * th) independent draws)
+    counts = torch.bincount(view, minlength=v).float() / batch
+    assert float((counts - 1.0 / v).abs().max()) < (0.03 if tile == (1, 1) else 0.12)
+    assert abs(float(x.float().mean()) / (w - 1) - 0.5) < 0.06 and abs(float(y.float().mean()) / (h - 1) - 0.5) < 0.06
+    # reproducible from the seed, different with another one; the public helper returns Rays + pixels
+    o2, _, _, idx2 = _kernels.sample_ray_batch(rot, tr, images, h, w, focal, batch, tile=tile, seed=99, want_indices=True)
+    _, _, _, idx3 = _kernels.sample_ray_batch(rot, tr, images, h, w, focal, batch, tile=tile, seed=100, want_indices=True)
+    assert torch.equal(idx, idx2) and not torch.equal(idx, idx3)
+    rays, pixels = sample_training_ray_batch(poses, intr, images, 1024, tile=tile, seed=5)
+    assert tuple(rays.origins.shape) == (1024, 3) and tuple(pixels.shape) == (1024, 3)
+    with pytest.raises(RuntimeError, match="multiple of the tile size"):
+        _kernels.sample_ray_batch(rot, tr, images, h, w, focal, 33, tile=(8, 4))

@@ -484,3 +484,38 @@ print("SHIM_OK")
     env = dict(os.environ, THRE3D_ATOM_REFERENCE=reference)
     out = subprocess.run([sys.executable, "-c", code, str(root), reference], capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0 and "SHIM_OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_checkpoints_saved_through_the_shim_use_reference_names(tmp_path):
+    """reference modules/volumetric_model.py:83-97 pickles the render procedure, the config type and NamedTuples by qualified
+    name: saved while the compat shim is active they must name ``thre3d_atom.*`` (loadable by the upstream framework), and
+    load back here."""
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    code = r'''
+import sys, pickletools, io
+sys.path.insert(0, sys.argv[1] + "/compat"); sys.path.insert(0, sys.argv[1])
+import torch, thre3d_atom
+from thre3d_atom.thre3d_reprs.voxels import VoxelGrid, VoxelSize
+from thre3d_atom.thre3d_reprs.renderers import render_sh_voxel_grid, SHVoxGridRenderConfig
+from thre3d_atom.modules.volumetric_model import VolumetricModel, create_volumetric_model_from_saved_model
+from thre3d_atom.utils.imaging_utils import CameraBounds
+assert render_sh_voxel_grid.__module__ == "thre3d_atom.thre3d_reprs.renderers" and VoxelSize.__module__ == "thre3d_atom.thre3d_reprs.voxels"
+grid = VoxelGrid(torch.rand(4, 4, 4, 1), torch.rand(4, 4, 4, 27), VoxelSize(0.5, 0.5, 0.5), tunable=True)
+vm = VolumetricModel(grid, render_sh_voxel_grid, SHVoxGridRenderConfig(8, CameraBounds(1.0, 2.0)), device=torch.device("cpu"))
+path = sys.argv[2]
+torch.save(vm.get_save_info({"camera_bounds": CameraBounds(1.0, 2.0)}), path)
+import zipfile
+raw = zipfile.ZipFile(path).read([n for n in zipfile.ZipFile(path).namelist() if n.endswith("data.pkl")][0])
+names = {arg for op, arg, _ in pickletools.genops(raw) if op.name in ("GLOBAL", "STACK_GLOBAL", "SHORT_BINUNICODE", "BINUNICODE") and isinstance(arg, str)}
+assert not any("thr3ed_atom_b200" in n for n in names), sorted(n for n in names if "thr3ed" in n)
+assert any(n.startswith("thre3d_atom.thre3d_reprs.renderers") for n in names)
+back, extra = create_volumetric_model_from_saved_model(path, thre3d_repr_creator=__import__("thre3d_atom.thre3d_reprs.voxels", fromlist=["x"]).create_voxel_grid_from_saved_info_dict, device=torch.device("cpu"))
+assert torch.equal(back.thre3d_repr.features, grid.features) and back.render_procedure is render_sh_voxel_grid
+print("NAMES_OK")
+'''
+    out = subprocess.run([sys.executable, "-c", code, str(root), str(tmp_path / "ckpt.pth")], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "NAMES_OK" in out.stdout, out.stdout + out.stderr

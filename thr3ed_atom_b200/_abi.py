@@ -52,6 +52,18 @@ class R3dCamera(C.Structure):
     ]
 
 
+class R3dViewSet(C.Structure):
+    _fields_ = [
+        ("rotations", C.c_void_p),
+        ("translations", C.c_void_p),
+        ("images", C.c_void_p),
+        ("num_views", C.c_int32),
+        ("height", C.c_int32),
+        ("width", C.c_int32),
+        ("focal", C.c_float),
+    ]
+
+
 class R3dRays(C.Structure):
     _fields_ = [
         ("origins", C.c_void_p),
@@ -102,6 +114,7 @@ SIGNATURES = {
          C.POINTER(R3dRenderOutGrad), C.POINTER(R3dGridGrad), C.c_void_p],
     ),
     "r3d_cast_rays": (C.c_int, [C.POINTER(R3dCamera), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "r3d_sample_ray_batch": (C.c_int, [C.POINTER(R3dViewSet), C.c_int64, C.c_int32, C.c_int32, C.c_uint64] + [C.c_void_p] * 5),
     "r3d_grid_lookup_fwd": (C.c_int, [C.POINTER(R3dGrid), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "r3d_grid_lookup_bwd": (C.c_int, [C.POINTER(R3dGrid), C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(R3dGridGrad), C.c_void_p]),
     "r3d_mark_touched_voxels": (C.c_int, [C.POINTER(R3dGrid), C.POINTER(R3dRays), C.POINTER(R3dRenderConfig), C.c_void_p, C.c_void_p]),

@@ -394,3 +394,31 @@ def multimem_adam_step(grad_multicast_ptr: int, param_multicast_ptr: int, param_
 def has_ab_variants() -> bool:
     """Was the loaded library built with -DR3D_AB_VARIANTS (measurement-only kernel variants selectable)?"""
     return bool(_abi.lib().r3d_has_ab_variants())
+
+
+def sample_ray_batch(rotations: Tensor, translations: Tensor, images: Optional[Tensor], height: int, width: int, focal: float, batch: int,
+                     tile: Tuple[int, int] = (1, 1), seed: int = 0, want_indices: bool = False):
+    """``batch`` training rays (+ target pixels) from random pixels / pixel tiles of ``V`` posed views (``r3d_sample_ray_batch``).
+    ``rotations [V, 3, 3]``, ``translations [V, 3]`` and ``images [V, H, W, 3]`` are fp32 CUDA tensors; ``tile = (width, height)``."""
+    rot = _require_cuda(rotations, "rotations").reshape(-1, 9).contiguous()
+    tr = _require_cuda(translations, "translations").reshape(-1, 3).contiguous()
+    v = rot.shape[0]
+    if tr.shape[0] != v:
+        raise ValueError("rotations and translations disagree on the number of views")
+    device = rot.device
+    if images is not None:
+        images = _require_cuda(images, "images")
+        if tuple(images.shape) != (v, height, width, 3) or not images.is_contiguous():
+            raise ValueError(f"images must be a contiguous [{v}, {height}, {width}, 3] tensor")
+    views = _abi.R3dViewSet(rot.data_ptr(), tr.data_ptr(), _ptr(images), v, int(height), int(width), float(focal))
+    origins = torch.empty((batch, 3), dtype=torch.float32, device=device)
+    directions = torch.empty((batch, 3), dtype=torch.float32, device=device)
+    pixels = torch.empty((batch, 3), dtype=torch.float32, device=device) if images is not None else None
+    indices = torch.empty((batch,), dtype=torch.int64, device=device) if want_indices else None
+    with torch.cuda.device(device):
+        _abi.check(
+            _abi.lib().r3d_sample_ray_batch(C.byref(views), batch, int(tile[0]), int(tile[1]), int(seed) & 0xFFFFFFFFFFFFFFFF,
+                                            origins.data_ptr(), directions.data_ptr(), _ptr(pixels), _ptr(indices), _stream(device)),
+            "r3d_sample_ray_batch",
+        )
+    return origins, directions, pixels, indices

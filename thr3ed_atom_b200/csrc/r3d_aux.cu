@@ -130,6 +130,62 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
 
 using namespace r3d;
 
+// ---- training-batch sampler: rays + target pixels of random pixels (or random 8x4 pixel tiles) of a set of posed views ----
+// Replaces, per training iteration, cast_rays for every cached view + randperm over all their pixels + three gathers
+// (reference modules/trainers.py:281-303, rendering/volumetric/utils/misc.py:117-129): nothing of size V*H*W is touched.
+__global__ void __launch_bounds__(256) sample_ray_batch_kernel(const float* __restrict__ rot, const float* __restrict__ trans,
+                                                               const float* __restrict__ images, int V, int H, int W, float focal,
+                                                               long long batch, int tile_w, int tile_h, unsigned seed_lo, unsigned seed_hi,
+                                                               float* __restrict__ origins, float* __restrict__ directions,
+                                                               float* __restrict__ pixels, long long* __restrict__ indices) {
+  const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (t >= batch) return;
+  const int per_tile = tile_w * tile_h;
+  const long long pick = t / per_tile;  // one random draw per tile (per pixel when the tile is 1x1)
+  const int in_tile = (int)(t % per_tile);
+  const unsigned key = ray_rng_key(seed_lo, seed_hi, pick);
+  const unsigned r0 = mix32(key + 0x9E3779B9U), r1 = mix32(key + 2u * 0x9E3779B9U), r2 = mix32(key + 3u * 0x9E3779B9U);
+  const int tiles_x = W / tile_w, tiles_y = H / tile_h;  // whole tiles only (checked on the host)
+  const int v = (int)(((unsigned long long)r0 * (unsigned)V) >> 32);
+  const int tx = (int)(((unsigned long long)r1 * (unsigned)tiles_x) >> 32), ty = (int)(((unsigned long long)r2 * (unsigned)tiles_y) >> 32);
+  const int x = tx * tile_w + in_tile % tile_w, y = ty * tile_h + in_tile / tile_w;
+  R3dCamera cam;
+  cam.height = H, cam.width = W, cam.focal = focal;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) cam.rotation[k] = __ldg(rot + 9 * v + k);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) cam.translation[k] = __ldg(trans + 3 * v + k);
+  Ray r;
+  camera_ray(cam, x, y, r);  // bit-identical to cast_rays for that pixel
+  origins[3 * t] = r.ox, origins[3 * t + 1] = r.oy, origins[3 * t + 2] = r.oz;
+  directions[3 * t] = r.dx, directions[3 * t + 1] = r.dy, directions[3 * t + 2] = r.dz;
+  const long long flat = ((long long)v * H + y) * W + x;
+  if (pixels && images) {
+    pixels[3 * t] = __ldg(images + 3 * flat), pixels[3 * t + 1] = __ldg(images + 3 * flat + 1), pixels[3 * t + 2] = __ldg(images + 3 * flat + 2);
+  }
+  if (indices) indices[t] = flat;
+}
+
+extern "C" int r3d_sample_ray_batch(const R3dViewSet* views, int64_t batch, int32_t tile_width, int32_t tile_height, uint64_t seed,
+                                    float* origins, float* directions, float* pixels, int64_t* indices, void* cuda_stream) {
+  if (!views || !views->rotations || !views->translations) return fail(R3D_ERR_INVALID_ARGUMENT, "r3d_sample_ray_batch: views / poses are NULL");
+  if (views->num_views < 1 || views->height < 1 || views->width < 1 || !(views->focal > 0.f))
+    return fail(R3D_ERR_INVALID_ARGUMENT, "r3d_sample_ray_batch: bad view set (%d views of %dx%d)", views->num_views, views->height, views->width);
+  if (tile_width < 1 || tile_height < 1 || views->width % tile_width != 0 || views->height % tile_height != 0)
+    return fail(R3D_ERR_INVALID_ARGUMENT, "r3d_sample_ray_batch: the image (%dx%d) must be a whole number of %dx%d tiles", views->height,
+                views->width, tile_height, tile_width);
+  if (batch < 0 || batch % ((int64_t)tile_width * tile_height) != 0)
+    return fail(R3D_ERR_INVALID_ARGUMENT, "r3d_sample_ray_batch: batch (%lld) must be a multiple of the tile size", (long long)batch);
+  if (batch == 0) return R3D_OK;
+  if (!origins || !directions) return fail(R3D_ERR_INVALID_ARGUMENT, "r3d_sample_ray_batch: output buffers are NULL");
+  if (pixels && !views->images) return fail(R3D_ERR_INVALID_ARGUMENT, "r3d_sample_ray_batch: pixels requested but views->images is NULL");
+  const long long blocks = (batch + 255) / 256;
+  sample_ray_batch_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+      views->rotations, views->translations, views->images, views->num_views, views->height, views->width, views->focal, batch, tile_width,
+      tile_height, (unsigned)(seed & 0xffffffffu), (unsigned)(seed >> 32), origins, directions, pixels, reinterpret_cast<long long*>(indices));
+  return check_launch("r3d_sample_ray_batch");
+}
+
 // ---- density quad volume (r3d_device.cuh: CellQ / density_pre_interp_q) ----
 __global__ void __launch_bounds__(256) quads_build_kernel(const float* __restrict__ dens, float4* __restrict__ quads, int W, int D, int H,
                                                           int pre, unsigned total) {
