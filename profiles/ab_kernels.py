@@ -105,6 +105,7 @@ def main():
                 "bwd_ms": sum(a.elapsed_time(b) for a, b in ev["bwd"]) / len(ev["bwd"]),
                 "max_abs_colour_diff_vs_first": float((col - ref_colour).abs().max()),
                 "grad_feat_l2": float(gf.double().norm()) if gf is not None else None,
+                "colour_sum": float(col.double().sum()), "colour_sq": float((col.double() ** 2).sum()),
             })
             print(json.dumps(results[-1]), file=sys.stderr, flush=True)
         del grid, vol_mod, rays, pixels, params

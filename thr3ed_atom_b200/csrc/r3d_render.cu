@@ -37,7 +37,12 @@
 // (backward) and keep all 32 lanes on contributing samples (forward).
 #include "r3d_host.h"
 
+#include <cuda.h>  // CUtensorMap (type and enums only: the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include <cstdlib>
+#include <map>
+#include <mutex>
+#include <tuple>
 
 // resident CTAs per SM the cooperative kernels are compiled for (register budget = 65536 / (128 * blocks)).
 // Measured at c3 on the B200: backward 7.95 ms at 4 CTAs/SM, 7.45 ms at 5 (96 registers, a few bytes of spill);
@@ -608,8 +613,62 @@ struct alignas(16) FwdGroupSmem {  // one per warp
 // gathered by DIFFERENT lane groups in the SAME load instruction, and lanes that name the same address are served by
 // one L1 wavefront: a cell shared by several samples of a marching step then crosses the L1 data pipe once per
 // instruction instead of once per sample.
-template <int DEG, bool DUAL, bool SORT = false>
-__global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_FWD_BLOCKS) render_fwd_group_kernel(const GridP g, const RaysP rp, const CfgP c, const OutP out) {
+// PF: software prefetch.  The gather of a marching step waits for its slowest sector, and ~8 % of a step's sectors are first
+// touches that come from DRAM (L2 hit rate 46 %): every lane-group iteration then costs a full DRAM latency although HBM is
+// 90 % idle.  The NEXT sample's position is known one step ahead (its depth is already computed for this sample's interval),
+// so each lane requests the lines of the cell it will land in -- 4 (x, y) columns of two z-adjacent records = 224 contiguous
+// bytes each -- into L2 (PF >= 1) and, with PF == 2, the 8 density words into L1, a whole marching step before they are
+// needed.  The cell is computed without the reference's exact rounding: a prefetch is a hint, results cannot change.
+//
+// TMA: density bricks through the Tensor Memory Accelerator.  The probe is the other global-memory round trip of a marching
+// step (8 scattered 4-byte loads per lane, ~400 cycles on an L2 hit) and on trained grids -- mostly empty space -- it is the
+// whole forward.  The next sample's depth is already known when a step starts, so the warp computes the cells its 32 rays
+// will land in at step i + 1, takes their bounding box (redux.sync min / max) and one elected lane issues ONE
+// cp.async.bulk.tensor.3d copy (SASS UTMALDG) of that kTmaBox brick of the density volume into a double-buffered
+// shared-memory slot of the warp (1.1 KB), completion on an mbarrier.  At step i + 1 the 8 corner densities are 8 LDS at
+// immediate offsets from one base: no address arithmetic, no clamping, no validity logic -- out-of-range box elements are
+// zero-filled by the TMA unit, which IS grid_sample's zero padding (voxels.py:296-303) -- and the position / cell arithmetic
+// of step i + 1 is the arithmetic the look-ahead already did.  The same box coordinates drive one
+// cp.async.bulk.prefetch.tensor.4d (SASS UTMAPF) of the feature records into L2, replacing the per-lane prefetch of PF
+// (which cost 15 % more instructions than it saved).  Boxes that do not fit (1 % of the steps at the BASELINE shapes, every
+// step of an incoherent ray batch) and the first step of a ray fall back to the direct loads; values are bit-identical
+// either way (same 8 numbers, same order of accumulation).
+constexpr int kTmaBoxX = 6, kTmaBoxY = 6, kTmaBoxZ = 8;  // voxels; z is the contiguous axis: 8 floats = 32 bytes per box row
+
+__device__ __forceinline__ void tma_load_box3(void* smem_dst, const CUtensorMap* map, int cz, int cy, int cx, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(smem_dst)),
+               "l"(map), "r"(cz), "r"(cy), "r"(cx), "r"((unsigned)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_box4(const CUtensorMap* map, int c0, int cz, int cy, int cx) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(map), "r"(c0), "r"(cz), "r"(cy), "r"(cx) : "memory");
+}
+__device__ __forceinline__ void tma_mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void tma_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_mbar_wait(unsigned long long* bar, unsigned parity) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  for (unsigned spin = 0;; ++spin) {
+    unsigned ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(a), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (spin > (1u << 24)) __trap();  // a protocol bug must be a CUDA error, never a hung GPU
+  }
+}
+
+template <int DEG, bool DUAL, bool SORT, int PF, bool TMA>
+__device__ __forceinline__ void fwd_group_body(const GridP& g, const RaysP& rp, const CfgP& c, const OutP& out, const CUtensorMap* dmap,
+                                               const CUtensorMap* fmap) {
   using H = FwdGroupShape<DEG>;
   using S = CoopShape<DEG>;
   constexpr int K = S::K, F = S::F, NV = S::NV, LPR = H::LPR, MPI = H::MPI;
@@ -617,6 +676,18 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_FWD_BLOCKS) render_fwd
   __shared__ __align__(16) FwdGroupSmem<DEG, DUAL> smem_all[4];
   FwdGroupSmem<DEG, DUAL>& sm = smem_all[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
+  constexpr int kBoxFloats = kTmaBoxX * kTmaBoxY * kTmaBoxZ;
+  __shared__ __align__(128) float dbox_all[TMA ? 4 * 2 * kBoxFloats : 1];
+  __shared__ __align__(8) unsigned long long dbar_all[TMA ? 8 : 1];
+  float* const dbox = dbox_all + (TMA ? (threadIdx.x >> 5) * 2 * kBoxFloats : 0);
+  unsigned long long* const dbar = dbar_all + (TMA ? (threadIdx.x >> 5) * 2 : 0);
+  if constexpr (TMA) {
+    if (lane == 0) {
+      tma_mbar_init(&dbar[0], 1), tma_mbar_init(&dbar[1], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+  }
 
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long ray = thread_to_ray(rp, t);
@@ -679,6 +750,13 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_FWD_BLOCKS) render_fwd
   bool have_z = false;
   DepthMarch dm;
   dm.bm = dm.bc = 0.f;
+  // TMA look-ahead state: this lane's next sample (inside test + cell), the warp's next brick (origin, validity), the slot
+  // it lands in and the mbarrier phases of the two slots
+  bool have_next = false, nx_inside = false, nx_box_ok = false;
+  CellQ nx_cq;
+  nx_cq.ix = nx_cq.iy = nx_cq.iz = 0;
+  int nx_bx = 0, nx_by = 0, nx_bz = 0, cur = 0;
+  unsigned phase = 0u;
   for (int i = lo; i <= hi; ++i) {
     // ---- per-lane: position, inside test, cell, density ----
     bool contributes = false;
@@ -686,18 +764,135 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_FWD_BLOCKS) render_fwd
     bool last = false;
     Cell cell;
     const bool mine = marching && i >= s.i_lo && i <= s.i_hi;
-    if (mine) {
-      if (!have_z) dm.start(s.dg, i), z = dm.next(s.dg, i), have_z = true;
-      last = (i == c.S - 1);
-      zn = last ? 0.0f : dm.next(s.dg, i + 1);
-      const float px = __fadd_rn(r.ox, __fmul_rn(r.dx, z));
-      const float py = __fadd_rn(r.oy, __fmul_rn(r.dy, z));
-      const float pz = __fadd_rn(r.oz, __fmul_rn(r.dz, z));
-      if (inside_aabb(g, px, py, pz)) {
-        make_cell_inside(g, px, py, pz, cell);
-        float dpost;
-        sigma = density_post(g.post, density_pre_interp<true>(g, cell), dpost);
-        contributes = sigma != 0.0f;
+    if constexpr (!TMA) {
+      if (mine) {
+        if (!have_z) dm.start(s.dg, i), z = dm.next(s.dg, i), have_z = true;
+        last = (i == c.S - 1);
+        zn = last ? 0.0f : dm.next(s.dg, i + 1);
+        const float px = __fadd_rn(r.ox, __fmul_rn(r.dx, z));
+        const float py = __fadd_rn(r.oy, __fmul_rn(r.dy, z));
+        const float pz = __fadd_rn(r.oz, __fmul_rn(r.dz, z));
+        if (inside_aabb(g, px, py, pz)) {
+          make_cell_inside(g, px, py, pz, cell);
+          float dpost;
+          sigma = density_post(g.post, density_pre_interp<true>(g, cell), dpost);
+          contributes = sigma != 0.0f;
+        }
+      }
+    } else {
+      // ---- this step's brick (requested one step ago) ----
+      const bool box_now = nx_box_ok;
+      if (box_now) {
+        tma_mbar_wait(&dbar[cur], (phase >> cur) & 1u);
+        phase ^= 1u << cur;
+      }
+      if (mine) {
+        if (!have_z) dm.start(s.dg, i), z = dm.next(s.dg, i), have_z = true;
+        last = (i == c.S - 1);
+        zn = last ? 0.0f : dm.next(s.dg, i + 1);
+        bool inside;
+        CellQ cq;
+        if (have_next) {  // position, inside test and cell of this sample were formed by the previous step's look-ahead
+          inside = nx_inside, cq = nx_cq;
+        } else {
+          const float px = __fadd_rn(r.ox, __fmul_rn(r.dx, z));
+          const float py = __fadd_rn(r.oy, __fmul_rn(r.dy, z));
+          const float pz = __fadd_rn(r.oz, __fmul_rn(r.dz, z));
+          inside = inside_aabb(g, px, py, pz);
+          if (inside) make_cell_q(g, px, py, pz, cq);
+        }
+        if (inside) {
+          float pre;
+          if (box_now && have_next) {
+            // 8 corner densities of the cell from the warp's brick: one base, immediate offsets, zero-filled outside the grid
+            const float* b0 = dbox + cur * kBoxFloats + ((cq.ix - nx_bx) * kTmaBoxY + (cq.iy - nx_by)) * kTmaBoxZ + (cq.iz - nx_bz);
+            const float* b1 = b0 + kTmaBoxY * kTmaBoxZ;
+            const bool ab = g.pre == R3D_PRE_ABS;
+            float sacc = 0.0f;
+            float wxy = cq.wx[0] * cq.wy[0];
+            float v0 = b0[0], v1 = b0[1];
+            if (ab) v0 = fabsf(v0), v1 = fabsf(v1);
+            sacc = fmaf(wxy * cq.wz[0], v0, sacc), sacc = fmaf(wxy * cq.wz[1], v1, sacc);
+            wxy = cq.wx[0] * cq.wy[1];
+            v0 = b0[kTmaBoxZ], v1 = b0[kTmaBoxZ + 1];
+            if (ab) v0 = fabsf(v0), v1 = fabsf(v1);
+            sacc = fmaf(wxy * cq.wz[0], v0, sacc), sacc = fmaf(wxy * cq.wz[1], v1, sacc);
+            wxy = cq.wx[1] * cq.wy[0];
+            v0 = b1[0], v1 = b1[1];
+            if (ab) v0 = fabsf(v0), v1 = fabsf(v1);
+            sacc = fmaf(wxy * cq.wz[0], v0, sacc), sacc = fmaf(wxy * cq.wz[1], v1, sacc);
+            wxy = cq.wx[1] * cq.wy[1];
+            v0 = b1[kTmaBoxZ], v1 = b1[kTmaBoxZ + 1];
+            if (ab) v0 = fabsf(v0), v1 = fabsf(v1);
+            sacc = fmaf(wxy * cq.wz[0], v0, sacc), sacc = fmaf(wxy * cq.wz[1], v1, sacc);
+            pre = sacc * (ab ? fabsf(g.dscale) : g.dscale);
+            float dpost;
+            sigma = density_post(g.post, pre, dpost);
+            contributes = sigma != 0.0f;
+            if (contributes) cell_from_q(g, cq, cell);
+          } else {
+            cell_from_q(g, cq, cell);
+            float dpost;
+            sigma = density_post(g.post, density_pre_interp<true>(g, cell), dpost);
+            contributes = sigma != 0.0f;
+          }
+        }
+      }
+      // ---- look-ahead: where do the warp's rays land at step i + 1?  One brick request for all of them. ----
+      have_next = mine && !last && (i + 1 <= s.i_hi);
+      nx_inside = false;
+      if (have_next) {
+        const float qx = __fadd_rn(r.ox, __fmul_rn(r.dx, zn));
+        const float qy = __fadd_rn(r.oy, __fmul_rn(r.dy, zn));
+        const float qz = __fadd_rn(r.oz, __fmul_rn(r.dz, zn));
+        nx_inside = inside_aabb(g, qx, qy, qz);
+        if (nx_inside) make_cell_q(g, qx, qy, qz, nx_cq);
+      }
+      const bool want = have_next && nx_inside;
+      const unsigned any = __ballot_sync(FULL, want);
+      cur ^= 1;
+      nx_box_ok = false;
+      if (any != 0u) {
+        const int big = 0x3fffffff;
+        const int mnx = __reduce_min_sync(FULL, want ? nx_cq.ix : big), mxx = __reduce_max_sync(FULL, want ? nx_cq.ix : -big);
+        const int mny = __reduce_min_sync(FULL, want ? nx_cq.iy : big), mxy = __reduce_max_sync(FULL, want ? nx_cq.iy : -big);
+        const int mnz = __reduce_min_sync(FULL, want ? nx_cq.iz : big), mxz = __reduce_max_sync(FULL, want ? nx_cq.iz : -big);
+        // a cell needs voxels i0 and i0 + 1 on every axis; the box origin along the contiguous axis must keep every box row
+        // 16-byte aligned in global memory (TMA moves 16-byte granules): z origin = a multiple of 4 floats
+        const int oz = mnz & ~3;
+        if (mxx - mnx + 2 <= kTmaBoxX && mxy - mny + 2 <= kTmaBoxY && mxz - oz + 2 <= kTmaBoxZ) {
+          nx_box_ok = true, nx_bx = mnx, nx_by = mny, nx_bz = oz;
+          if (lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the slot's last generic-proxy reads (two steps ago) precede the copy
+            tma_mbar_expect_tx(&dbar[cur], (unsigned)(kBoxFloats * sizeof(float)));
+            tma_load_box3(dbox + cur * kBoxFloats, dmap, oz, mny, mnx, &dbar[cur]);
+            if (fmap != nullptr) tma_prefetch_box4(fmap, 0, oz, mny, mnx);
+          }
+        }
+      }
+    }
+    if constexpr (PF != 0) {
+      if (mine && !last) {
+        const float qx = fmaf(r.dx, zn, r.ox), qy = fmaf(r.dy, zn, r.oy), qz = fmaf(r.dz, zn, r.oz);
+        if (inside_aabb(g, qx, qy, qz)) {
+          const float gx = (fmaf(qx, g.ns[0], g.nb[0]) + 1.0f) * (0.5f * (float)g.W) - 0.5f;
+          const float gy = (fmaf(qy, g.ns[1], g.nb[1]) + 1.0f) * (0.5f * (float)g.D) - 0.5f;
+          const float gz = (fmaf(qz, g.ns[2], g.nb[2]) + 1.0f) * (0.5f * (float)g.H) - 0.5f;
+          const int x0 = min(max((int)floorf(gx), 0), max(g.W - 2, 0)), y0 = min(max((int)floorf(gy), 0), max(g.D - 2, 0));
+          const int z0 = min(max((int)floorf(gz), 0), max(g.H - 2, 0));
+          const unsigned v00 = (unsigned)((x0 * g.D + y0) * g.H + z0);
+          const unsigned dy = (unsigned)(g.D > 1 ? g.H : 0), dx = (unsigned)(g.W > 1 ? g.D * g.H : 0);
+          const unsigned cols[4] = {v00, v00 + dy, v00 + dx, v00 + dx + dy};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const char* col = reinterpret_cast<const char*>(g.feat) + 16ull * ((unsigned long long)cols[q] * stride4);
+            // records z0 and z0 + 1 of the column: 2 * stride floats, at most three 128-byte lines
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(col));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(col + 4 * g.stride));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(col + 8 * g.stride - 4));
+            if constexpr (PF == 2) asm volatile("prefetch.global.L1 [%0];" ::"l"(g.dens + cols[q]));  // z0 and z0 + 1 share a sector almost always
+          }
+        }
       }
     }
     const unsigned act = __ballot_sync(FULL, contributes);
@@ -869,6 +1064,22 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_FWD_BLOCKS) render_fwd
     out.disparity[ray] = __fdiv_rn(1.0f, m);
   }
 }
+
+template <int DEG, bool DUAL, bool SORT = false, int PF = 0>
+__global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_FWD_BLOCKS) render_fwd_group_kernel(const GridP g, const RaysP rp, const CfgP c, const OutP out) {
+  fwd_group_body<DEG, DUAL, SORT, PF, false>(g, rp, c, out, nullptr, nullptr);
+}
+
+#ifdef R3D_AB_VARIANTS
+// the same kernel with TMA density bricks (+ TMA L2 prefetch of the feature bricks when `feat_prefetch` is set): measured
+// slower than the direct loads, kept in the measurement build
+template <int DEG, bool DUAL>
+__global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_FWD_BLOCKS)
+    render_fwd_group_tma_kernel(const GridP g, const RaysP rp, const CfgP c, const OutP out, const __grid_constant__ CUtensorMap dens_map,
+                                const __grid_constant__ CUtensorMap feat_map, const int feat_prefetch) {
+  fwd_group_body<DEG, DUAL, false, 0, true>(g, rp, c, out, &dens_map, feat_prefetch ? &feat_map : nullptr);
+}
+#endif
 
 #ifdef R3D_AB_VARIANTS
 }  // namespace r3d
@@ -1418,6 +1629,62 @@ __global__ void __launch_bounds__(128) sample_stats_kernel(const GridP g, const 
 // =================================================================================================
 // host-side dispatch
 // =================================================================================================
+#ifdef R3D_AB_VARIANTS
+// ---- tensor maps of the TMA forward (density volume [W][D][H] fp32, feature volume [W][D][H][stride] fp32) ----
+struct TmaMaps {
+  CUtensorMap dens, feat;
+  bool ok;
+};
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn tma_encoder() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+    cudaGetLastError();
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// The maps depend on the buffers' addresses and shapes only; they are cached (the one piece of state the library keeps,
+// behind a mutex) and re-encoded when a grid of another shape or at another address shows up.
+static const TmaMaps& tma_maps_for(const GridP& g) {
+  static std::mutex mu;
+  static std::map<std::tuple<const void*, const void*, int, int, int, int>, TmaMaps> cache;
+  std::lock_guard<std::mutex> lock(mu);
+  const auto key = std::make_tuple((const void*)g.dens, (const void*)g.feat, g.W, g.D, g.H, g.stride);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  if (cache.size() > 64) cache.clear();
+  TmaMaps m;
+  m.ok = false;
+  EncodeTiledFn enc = tma_encoder();
+  // strides must be multiples of 16 bytes: H % 4 == 0 for the density volume; the record stride is one already
+  if (enc && g.H % 4 == 0 && g.stride % 4 == 0 && (reinterpret_cast<uintptr_t>(g.dens) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.feat) & 15) == 0) {
+    const cuuint64_t ddim[3] = {(cuuint64_t)g.H, (cuuint64_t)g.D, (cuuint64_t)g.W};
+    const cuuint64_t dstr[2] = {(cuuint64_t)g.H * 4, (cuuint64_t)g.D * g.H * 4};
+    const cuuint32_t dbox[3] = {(cuuint32_t)kTmaBoxZ, (cuuint32_t)kTmaBoxY, (cuuint32_t)kTmaBoxX};
+    const cuuint32_t one3[3] = {1, 1, 1};
+    const CUresult r1 = enc(&m.dens, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(g.dens), ddim, dstr, dbox, one3, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const cuuint64_t fdim[4] = {(cuuint64_t)g.stride, (cuuint64_t)g.H, (cuuint64_t)g.D, (cuuint64_t)g.W};
+    const cuuint64_t fstr[3] = {(cuuint64_t)g.stride * 4, (cuuint64_t)g.H * g.stride * 4, (cuuint64_t)g.D * g.H * g.stride * 4};
+    const cuuint32_t fbox[4] = {(cuuint32_t)g.stride, (cuuint32_t)kTmaBoxZ, (cuuint32_t)kTmaBoxY, (cuuint32_t)kTmaBoxX};
+    const cuuint32_t one4[4] = {1, 1, 1, 1};
+    const CUresult r2 = g.stride <= 256
+                            ? enc(&m.feat, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(g.feat), fdim, fstr, fbox, one4, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)
+                            : CUDA_ERROR_INVALID_VALUE;
+    m.ok = (r1 == CUDA_SUCCESS && r2 == CUDA_SUCCESS);
+  }
+  return cache.emplace(key, m).first->second;
+}
+
+#endif  // R3D_AB_VARIANTS
+
 // the lane-group forward addresses records with 32-bit float4 indices
 static bool group_indexable(const GridP& g) {
   return (unsigned long long)g.W * g.D * g.H * (unsigned long long)(g.stride / 4) <= 0xffffffffull;
@@ -1465,7 +1732,7 @@ static void launch_fwd(int vec, int variant, dim3 grid, cudaStream_t st, const G
       render_fwd_coop_kernel<DEG, false><<<grid, 128, 0, st>>>(g, r, c, o);
       return;
     }
-    if (group_indexable(g) && (variant & (32 | 2048))) {
+    if (group_indexable(g) && (variant & (32 | 2048 | 4096 | 8192))) {
       if ((variant & 96) == 96 && (variant & 256) && (variant & 1024))
         launch_fwd_ws<DEG, false, true, 1, true>(grid, st, g, r, c, o);
       else if ((variant & 96) == 96 && (variant & 1024))
@@ -1478,6 +1745,10 @@ static void launch_fwd(int vec, int variant, dim3 grid, cudaStream_t st, const G
         launch_fwd_ws<DEG, false, true>(grid, st, g, r, c, o);
       else if (variant & 32)
         launch_fwd_ws<DEG, false, false>(grid, st, g, r, c, o);
+      else if (variant & 8192)
+        render_fwd_group_kernel<DEG, false, false, 2><<<grid, 128, 0, st>>>(g, r, c, o);
+      else if (variant & 4096)
+        render_fwd_group_kernel<DEG, false, false, 1><<<grid, 128, 0, st>>>(g, r, c, o);
       else
         render_fwd_group_kernel<DEG, false, true><<<grid, 128, 0, st>>>(g, r, c, o);
       return;
@@ -1489,6 +1760,21 @@ static void launch_fwd(int vec, int variant, dim3 grid, cudaStream_t st, const G
   const bool per_ray = false;
 #endif
   if (vec != 0 && !diffuse && !per_ray && group_indexable(g)) {
+#ifdef R3D_AB_VARIANTS
+    // TMA density bricks need a coherent warp (an image tile per warp): image-shaped batches and in-kernel ray generation.
+    // $R3D_FWD_TMA: 0 = off (default: measured slower), 1 = density bricks, 2 = + feature-brick L2 prefetch
+    static const int tma_mode = [] {
+      const char* e = getenv("R3D_FWD_TMA");
+      return e ? atoi(e) : 0;
+    }();
+    if (tma_mode > 0 && r.tile_w > 0) {
+      const TmaMaps& m = tma_maps_for(g);
+      if (m.ok) {
+        render_fwd_group_tma_kernel<DEG, false><<<grid, 128, 0, st>>>(g, r, c, o, m.dens, m.feat, tma_mode > 1 ? 1 : 0);
+        return;
+      }
+    }
+#endif
     // tuning hook: $R3D_FWD_CARVEOUT = preferred shared-memory carve-out in percent (the rest of the 228 KB is L1)
     static const int carve = [] {
       const char* e = getenv("R3D_FWD_CARVEOUT");
