@@ -12,6 +12,8 @@
 // after); this function only enqueues the reduction kernel.
 #include "r3d_host.h"
 
+#include <cstdlib>
+
 namespace r3d {
 
 __global__ void __launch_bounds__(512) multimem_allreduce_kernel(float* __restrict__ mc, long long vec_begin, long long vec_end) {
@@ -62,11 +64,11 @@ __global__ void __launch_bounds__(512) multimem_allreduce_kernel(float* __restri
 // 7-streams-per-element optimizer pass over the whole grid disappears from every GPU, and so do 7/8 of its state.
 // The caller brackets the launch with cross-rank barriers (all gradients complete before; all parameters updated after).
 // ---------------------------------------------------------------------------------------------------------------------
+template <int UNROLL>
 __global__ void __launch_bounds__(512) multimem_adam_kernel(const float* __restrict__ grad_mc, float* __restrict__ param_mc,
                                                             const float* __restrict__ param_local, float* __restrict__ m, float* __restrict__ v,
                                                             long long vec_begin, long long vec_end, float step, float b1, float b2, float eps,
                                                             float bc2_sqrt, float gscale) {
-  constexpr int UNROLL = 4;
   const long long stride = (long long)gridDim.x * blockDim.x;
   auto update = [&](const float4& G, float4& P, float4& M, float4& V) {
 #define R3D_ADAM1(c)                                       \
@@ -160,9 +162,21 @@ extern "C" int r3d_multimem_adam_step(void* grad_multicast_ptr, void* param_mult
   int blocks = num_blocks > 0 ? num_blocks : sms * 2;
   const long long need = (end - begin + 511) / 512;
   if (blocks > need) blocks = (int)need;
-  multimem_adam_kernel<<<blocks, 512, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
-      static_cast<const float*>(grad_multicast_ptr), static_cast<float*>(param_multicast_ptr), param_local, exp_avg_shard, exp_avg_sq_shard, begin,
-      end, lr / bias_correction1, beta1, beta2, eps, sqrtf(bias_correction2), grad_scale);
+  // tuning hook: $R3D_MULTIMEM_UNROLL = independent 16-byte multimem loads in flight per thread (default 4)
+  static const int unroll = [] {
+    const char* e = getenv("R3D_MULTIMEM_UNROLL");
+    return e ? atoi(e) : 4;
+  }();
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  const float step = lr / bias_correction1, bc2s = sqrtf(bias_correction2);
+  const float* gmc = static_cast<const float*>(grad_multicast_ptr);
+  float* pmc = static_cast<float*>(param_multicast_ptr);
+  if (unroll >= 8)
+    multimem_adam_kernel<8><<<blocks, 512, 0, st>>>(gmc, pmc, param_local, exp_avg_shard, exp_avg_sq_shard, begin, end, step, beta1, beta2, eps, bc2s, grad_scale);
+  else if (unroll <= 2)
+    multimem_adam_kernel<2><<<blocks, 512, 0, st>>>(gmc, pmc, param_local, exp_avg_shard, exp_avg_sq_shard, begin, end, step, beta1, beta2, eps, bc2s, grad_scale);
+  else
+    multimem_adam_kernel<4><<<blocks, 512, 0, st>>>(gmc, pmc, param_local, exp_avg_shard, exp_avg_sq_shard, begin, end, step, beta1, beta2, eps, bc2s, grad_scale);
   return check_launch("r3d_multimem_adam_step");
 }
 

@@ -666,7 +666,7 @@ __device__ __forceinline__ void tma_mbar_wait(unsigned long long* bar, unsigned 
   }
 }
 
-template <int DEG, bool DUAL, bool SORT, int PF, bool TMA>
+template <int DEG, bool DUAL, bool SORT, int PF, bool TMA, bool LA = false>
 __device__ __forceinline__ void fwd_group_body(const GridP& g, const RaysP& rp, const CfgP& c, const OutP& out, const CUtensorMap* dmap,
                                                const CUtensorMap* fmap) {
   using H = FwdGroupShape<DEG>;
@@ -757,6 +757,12 @@ __device__ __forceinline__ void fwd_group_body(const GridP& g, const RaysP& rp, 
   nx_cq.ix = nx_cq.iy = nx_cq.iz = 0;
   int nx_bx = 0, nx_by = 0, nx_bz = 0, cur = 0;
   unsigned phase = 0u;
+  Cell la_cell;      // LA: the next sample's cell and its 8 corner densities (requested one step ahead)
+  float la_d[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) la_d[k] = 0.f;
+  la_cell.ox[0] = la_cell.ox[1] = la_cell.oy[0] = la_cell.oy[1] = la_cell.oz[0] = la_cell.oz[1] = 0;
+  la_cell.wx[0] = la_cell.wx[1] = la_cell.wy[0] = la_cell.wy[1] = la_cell.wz[0] = la_cell.wz[1] = 0.f;
   for (int i = lo; i <= hi; ++i) {
     // ---- per-lane: position, inside test, cell, density ----
     bool contributes = false;
@@ -764,7 +770,64 @@ __device__ __forceinline__ void fwd_group_body(const GridP& g, const RaysP& rp, 
     bool last = false;
     Cell cell;
     const bool mine = marching && i >= s.i_lo && i <= s.i_hi;
-    if constexpr (!TMA) {
+    if constexpr (LA) {
+      // register look-ahead: the 8 density loads of sample i + 1 are issued before the gather of sample i and consumed one
+      // iteration later, so the probe's global round trip overlaps the gather instead of preceding it
+      if (mine) {
+        if (!have_z) dm.start(s.dg, i), z = dm.next(s.dg, i), have_z = true;
+        last = (i == c.S - 1);
+        zn = last ? 0.0f : dm.next(s.dg, i + 1);
+        bool inside;
+        if (have_next) {
+          inside = nx_inside, cell = la_cell;
+          if (inside) {
+            float sacc = 0.0f;
+#pragma unroll
+            for (int ix = 0; ix < 2; ++ix)
+#pragma unroll
+              for (int iy = 0; iy < 2; ++iy) {
+                const float wxy = cell.wx[ix] * cell.wy[iy];
+                float v0 = la_d[4 * ix + 2 * iy], v1 = la_d[4 * ix + 2 * iy + 1];
+                if (g.pre == R3D_PRE_ABS) v0 = fabsf(v0), v1 = fabsf(v1);
+                sacc = fmaf(wxy * cell.wz[0], v0, sacc);
+                sacc = fmaf(wxy * cell.wz[1], v1, sacc);
+              }
+            float dpost;
+            sigma = density_post(g.post, sacc * (g.pre == R3D_PRE_ABS ? fabsf(g.dscale) : g.dscale), dpost);
+            contributes = sigma != 0.0f;
+          }
+        } else {
+          const float px = __fadd_rn(r.ox, __fmul_rn(r.dx, z));
+          const float py = __fadd_rn(r.oy, __fmul_rn(r.dy, z));
+          const float pz = __fadd_rn(r.oz, __fmul_rn(r.dz, z));
+          if (inside_aabb(g, px, py, pz)) {
+            make_cell_inside(g, px, py, pz, cell);
+            float dpost;
+            sigma = density_post(g.post, density_pre_interp<true>(g, cell), dpost);
+            contributes = sigma != 0.0f;
+          }
+        }
+      }
+      have_next = mine && !last && (i + 1 <= s.i_hi);
+      nx_inside = false;
+      if (have_next) {
+        const float qx = __fadd_rn(r.ox, __fmul_rn(r.dx, zn));
+        const float qy = __fadd_rn(r.oy, __fmul_rn(r.dy, zn));
+        const float qz = __fadd_rn(r.oz, __fmul_rn(r.dz, zn));
+        nx_inside = inside_aabb(g, qx, qy, qz);
+        if (nx_inside) {
+          make_cell_inside(g, qx, qy, qz, la_cell);
+#pragma unroll
+          for (int ix = 0; ix < 2; ++ix)
+#pragma unroll
+            for (int iy = 0; iy < 2; ++iy) {
+              const unsigned col = (unsigned)(la_cell.ox[ix] + la_cell.oy[iy]);
+              la_d[4 * ix + 2 * iy] = __ldg(g.dens + (col + (unsigned)la_cell.oz[0]));
+              la_d[4 * ix + 2 * iy + 1] = __ldg(g.dens + (col + (unsigned)la_cell.oz[1]));
+            }
+        }
+      }
+    } else if constexpr (!TMA) {
       if (mine) {
         if (!have_z) dm.start(s.dg, i), z = dm.next(s.dg, i), have_z = true;
         last = (i == c.S - 1);
@@ -1071,6 +1134,11 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_FWD_BLOCKS) render_fwd
 }
 
 #ifdef R3D_AB_VARIANTS
+// the same kernel with the density loads of sample i + 1 issued one step ahead (register look-ahead)
+template <int DEG, bool DUAL>
+__global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_FWD_BLOCKS) render_fwd_group_la_kernel(const GridP g, const RaysP rp, const CfgP c, const OutP out) {
+  fwd_group_body<DEG, DUAL, false, 0, false, true>(g, rp, c, out, nullptr, nullptr);
+}
 // the same kernel with TMA density bricks (+ TMA L2 prefetch of the feature bricks when `feat_prefetch` is set): measured
 // slower than the direct loads, kept in the measurement build
 template <int DEG, bool DUAL>
@@ -1732,7 +1800,7 @@ static void launch_fwd(int vec, int variant, dim3 grid, cudaStream_t st, const G
       render_fwd_coop_kernel<DEG, false><<<grid, 128, 0, st>>>(g, r, c, o);
       return;
     }
-    if (group_indexable(g) && (variant & (32 | 2048 | 4096 | 8192))) {
+    if (group_indexable(g) && (variant & (32 | 2048 | 4096 | 8192 | 16384))) {
       if ((variant & 96) == 96 && (variant & 256) && (variant & 1024))
         launch_fwd_ws<DEG, false, true, 1, true>(grid, st, g, r, c, o);
       else if ((variant & 96) == 96 && (variant & 1024))
@@ -1745,6 +1813,8 @@ static void launch_fwd(int vec, int variant, dim3 grid, cudaStream_t st, const G
         launch_fwd_ws<DEG, false, true>(grid, st, g, r, c, o);
       else if (variant & 32)
         launch_fwd_ws<DEG, false, false>(grid, st, g, r, c, o);
+      else if (variant & 16384)
+        render_fwd_group_la_kernel<DEG, false><<<grid, 128, 0, st>>>(g, r, c, o);
       else if (variant & 8192)
         render_fwd_group_kernel<DEG, false, false, 2><<<grid, 128, 0, st>>>(g, r, c, o);
       else if (variant & 4096)
