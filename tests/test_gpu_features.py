@@ -491,7 +491,8 @@ def test_cooperative_and_per_ray_kernels_agree(name, cuda_device, monkeypatch):
                                         ("ws-sort+L2 prefetch", 96 | 256, None), ("ws-sort+L1 prefetch", 96 | 512, None),
                                         ("group fwd, ws bwd", 128, None), ("ws fwd, ws bwd", 96 | 128, None),
                                         ("group-sort+cache", 2048, None), ("group-sort", 2048, "0"),
-                                        ("ws-sort+dual streams", 96 | 1024, None), ("ws-sort+L2 prefetch+dual streams", 96 | 256 | 1024, None)):
+                                        ("ws-sort+dual streams", 96 | 1024, None), ("ws-sort+L2 prefetch+dual streams", 96 | 256 | 1024, None),
+                                        ("split+cache", 32768, None), ("split, no quads", 32768, None), ("group-quads+cache", 65536, None)):
         if cache_limit is None:
             monkeypatch.delenv("R3D_SAMPLE_CACHE_MAX_BYTES", raising=False)
         else:
@@ -510,7 +511,10 @@ def test_cooperative_and_per_ray_kernels_agree(name, cuda_device, monkeypatch):
         if label.startswith("ws"):  # warp-specialised forward: the lane-group arithmetic (up to FMA contraction), any publish order
             assert (res[0] - results["group"][0]).abs().max().item() < 1e-6, label
             assert (res[0] - results["ws"][0]).abs().max().item() < 1e-6, label  # with / without cache, sorted or not, quads or not
-        if label.startswith("group") or label.startswith("ws"):
+        if label.startswith("split") or label.startswith("group-quads"):  # the lane-group arithmetic (up to FMA contraction)
+            assert (res[0] - results["group+cache"][0]).abs().max().item() < 1e-6, label
+            assert ((res[1] - results["group+cache"][1]).abs() <= 1e-6 * results["group+cache"][1].abs().clamp(min=1.0)).all(), label
+        if label.startswith("group") or label.startswith("ws") or label.startswith("split"):  # ("group-quads" included)
             assert (res[0] - ref[0]).abs().max().item() < 2e-6, label
             assert ((res[1] - ref[1]).abs() <= 2e-6 * ref[1].abs().clamp(min=1.0)).all(), label
         else:

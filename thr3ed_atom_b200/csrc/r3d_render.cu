@@ -9,7 +9,11 @@
 //                            forward's contribution ballots instead of repeating the density probe; DUAL: specular + diffuse
 //   render_bwd_kernel        backward, one thread per ray end to end (A/B)
 //   mark_touched_kernel      measurement helper (unique voxels referenced by a batch)
-// R3dRenderConfig.variant bits (A/B only): 1 per-ray backward, 2 per-ray forward, 4 TMA-staged forward, 8 cp.async-staged forward.
+// R3dRenderConfig.variant bits (A/B only, -DR3D_AB_VARIANTS): 1 per-ray backward, 2 per-ray forward, 4 TMA-staged forward,
+//   8 cp.async-staged forward, 32 warp-specialised forward (+64 sorted, +256/512 L2/L1 prefetch, +1024 dual-stream consumer),
+//   128 warp-specialised backward, 2048 lane-group + cell-sorted publish, 4096/8192 lane-group + next-sample prefetch,
+//   16384 lane-group + register look-ahead, 32768 two-kernel forward (r3d_fwd_split.cuh; $R3D_SPLIT_MODE picks the gather
+//   flavour), 65536 lane-group + density quad volume.  $R3D_FWD_TMA=1|2: TMA density bricks.
 //
 // Common structure.  One thread owns one ray and marches it front to back.  Per sample it
 //   1. forms the sample position exactly as the reference does (sample.py:54-67),
@@ -666,7 +670,7 @@ __device__ __forceinline__ void tma_mbar_wait(unsigned long long* bar, unsigned 
   }
 }
 
-template <int DEG, bool DUAL, bool SORT, int PF, bool TMA, bool LA = false>
+template <int DEG, bool DUAL, bool SORT, int PF, bool TMA, bool LA = false, bool DQ = false>
 __device__ __forceinline__ void fwd_group_body(const GridP& g, const RaysP& rp, const CfgP& c, const OutP& out, const CUtensorMap* dmap,
                                                const CUtensorMap* fmap) {
   using H = FwdGroupShape<DEG>;
@@ -825,6 +829,25 @@ __device__ __forceinline__ void fwd_group_body(const GridP& g, const RaysP& rp, 
               la_d[4 * ix + 2 * iy] = __ldg(g.dens + (col + (unsigned)la_cell.oz[0]));
               la_d[4 * ix + 2 * iy + 1] = __ldg(g.dens + (col + (unsigned)la_cell.oz[1]));
             }
+        }
+      }
+    } else if constexpr (DQ) {
+      // density quad volume (r3d_device.cuh): the 8 corner densities are two 16-byte loads, no clamps; the clamped offsets /
+      // zeroed weights of the cell are formed only for samples that go on to gather records
+      if (mine) {
+        if (!have_z) dm.start(s.dg, i), z = dm.next(s.dg, i), have_z = true;
+        last = (i == c.S - 1);
+        zn = last ? 0.0f : dm.next(s.dg, i + 1);
+        const float px = __fadd_rn(r.ox, __fmul_rn(r.dx, z));
+        const float py = __fadd_rn(r.oy, __fmul_rn(r.dy, z));
+        const float pz = __fadd_rn(r.oz, __fmul_rn(r.dz, z));
+        if (inside_aabb(g, px, py, pz)) {
+          CellQ cq;
+          make_cell_q(g, px, py, pz, cq);
+          float dpost;
+          sigma = density_post(g.post, density_pre_interp_q(g, cq), dpost);
+          contributes = sigma != 0.0f;
+          if (contributes) cell_from_q(g, cq, cell);
         }
       }
     } else if constexpr (!TMA) {
@@ -1134,6 +1157,11 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_FWD_BLOCKS) render_fwd
 }
 
 #ifdef R3D_AB_VARIANTS
+// the same kernel probing the density quad volume
+template <int DEG, bool DUAL>
+__global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_FWD_BLOCKS) render_fwd_group_dq_kernel(const GridP g, const RaysP rp, const CfgP c, const OutP out) {
+  fwd_group_body<DEG, DUAL, false, 0, false, false, true>(g, rp, c, out, nullptr, nullptr);
+}
 // the same kernel with the density loads of sample i + 1 issued one step ahead (register look-ahead)
 template <int DEG, bool DUAL>
 __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_FWD_BLOCKS) render_fwd_group_la_kernel(const GridP g, const RaysP rp, const CfgP c, const OutP out) {
@@ -1152,6 +1180,7 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 3 : R3D_FWD_BLOCKS)
 #ifdef R3D_AB_VARIANTS
 }  // namespace r3d
 #include "r3d_fwd_ws.cuh"
+#include "r3d_fwd_split.cuh"
 namespace r3d {
 #endif
 
@@ -1798,6 +1827,49 @@ static void launch_fwd(int vec, int variant, dim3 grid, cudaStream_t st, const G
     }
     if (variant & 8) {  // shared-memory staged gather (the default before the lane-group kernel)
       render_fwd_coop_kernel<DEG, false><<<grid, 128, 0, st>>>(g, r, c, o);
+      return;
+    }
+    if (group_indexable(g) && (variant & 32768) && o.mask && o.cache) {  // two-kernel forward (r3d_fwd_split.cuh)
+      static float* wplane = nullptr;
+      static size_t wplane_floats = 0;
+      const size_t need = (size_t)c.S * (size_t)r.n;
+      if (need > wplane_floats) {
+        if (wplane) cudaFree(wplane);
+        cudaMalloc(&wplane, need * sizeof(float));
+        wplane_floats = need;
+      }
+      if (g.quads)
+        render_fwd_probe_kernel<true><<<grid, 128, 0, st>>>(g, r, c, o, wplane);
+      else
+        render_fwd_probe_kernel<false><<<grid, 128, 0, st>>>(g, r, c, o, wplane);
+      static const int mode = [] {
+        const char* e = getenv("R3D_SPLIT_MODE");
+        return e ? atoi(e) : 0;
+      }();
+      static const int carve = [] {  // tuning hook: preferred shared-memory carve-out of the gather kernel in percent
+        const char* e = getenv("R3D_SPLIT_CARVEOUT");
+        const int v = e ? atoi(e) : -1;
+        if (v >= 0) {
+          cudaFuncSetAttribute(render_fwd_gather_kernel<DEG, 0, false>, cudaFuncAttributePreferredSharedMemoryCarveout, v);
+          cudaFuncSetAttribute(render_fwd_gather_kernel<DEG, 1, false>, cudaFuncAttributePreferredSharedMemoryCarveout, v);
+        }
+        return v;
+      }();
+      (void)carve;
+      switch (mode) {  // $R3D_SPLIT_MODE: prefetch flavour (0..3) + 10 for the run-merged gather
+        case 1: render_fwd_gather_kernel<DEG, 1, false><<<grid, 128, 0, st>>>(g, r, c, o, wplane); break;
+        case 2: render_fwd_gather_kernel<DEG, 2, false><<<grid, 128, 0, st>>>(g, r, c, o, wplane); break;
+        case 3: render_fwd_gather_kernel<DEG, 3, false><<<grid, 128, 0, st>>>(g, r, c, o, wplane); break;
+        case 9: render_fwd_gather_kernel<DEG, 9, false><<<grid, 128, 0, st>>>(g, r, c, o, wplane); break;
+        case 10: render_fwd_gather_kernel<DEG, 0, true><<<grid, 128, 0, st>>>(g, r, c, o, wplane); break;
+        case 11: render_fwd_gather_kernel<DEG, 1, true><<<grid, 128, 0, st>>>(g, r, c, o, wplane); break;
+        case 13: render_fwd_gather_kernel<DEG, 3, true><<<grid, 128, 0, st>>>(g, r, c, o, wplane); break;
+        default: render_fwd_gather_kernel<DEG, 0, false><<<grid, 128, 0, st>>>(g, r, c, o, wplane); break;
+      }
+      return;
+    }
+    if (group_indexable(g) && (variant & 65536) && g.quads) {  // lane-group kernel probing the density quad volume
+      render_fwd_group_dq_kernel<DEG, false><<<grid, 128, 0, st>>>(g, r, c, o);
       return;
     }
     if (group_indexable(g) && (variant & (32 | 2048 | 4096 | 8192 | 16384))) {

@@ -177,7 +177,7 @@ class _FusedSHVoxGridRender(torch.autograd.Function):
 
 def _probe_volume(grid: VoxelGrid, densities: Optional[Tensor], args: _kernels.RenderArgs) -> Optional[Tensor]:
     """Density quad volume for the warp-specialised forward kernel (None when another kernel will run)."""
-    if not (args.variant & 32) or args.diffuse:
+    if not (args.variant & (32 | 32768 | 65536)) or args.diffuse:
         return None
     return grid.density_quads(densities, fresh=args.keep_for_backward)
 
