@@ -360,8 +360,8 @@ def main():
     device = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL writes its version banner to stdout; stdout carries the one JSON line
+        # NCCL writes its debug output -- at any NCCL_DEBUG level its version banner -- to stdout; stdout carries the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
     assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
@@ -467,7 +467,7 @@ def main():
                 if sharded is not None:
                     sharded.close()
                 sharded = None
-            exchange = "fused" if sharded is not None else "nccl"
+            exchange = ("fused-" + sharded.exchange) if sharded is not None else "nccl"  # fused-multimem (in-switch) / fused-peer (2 ranks)
         elif want == "nvls" or (want in ("auto", "fused") and args.no_optimizer):
             from thr3ed_atom_b200.distributed import NVLSGradientReducer
 
@@ -683,7 +683,8 @@ def main():
         ms_per_step = total_ms / args.steps
         value = world * n_rays / (ms_per_step * 1e-3)  # weak: n_rays per rank; strong: n_rays is the rank's shard of one view
         opt_name = ("none" if args.no_optimizer else
-                    ("in-switch reduce-scatter -> shard-local Adam -> all-gather (r3d_multimem_adam_step)" if sharded is not None else
+                    (("peer-to-peer reduce-scatter -> shard-local Adam -> all-gather (r3d_peer_adam_step)" if sharded.exchange == "peer" else
+                      "in-switch reduce-scatter -> shard-local Adam -> all-gather (r3d_multimem_adam_step)") if sharded is not None else
                      (f"{exchange} all-reduce(grid grad) + " if world > 1 else "") + "fused dense Adam (r3d_adam_step)"))
         step_desc = "zero_grad + render_rays fwd + l1_loss + backward (fused bwd)"
         if args.no_optimizer:

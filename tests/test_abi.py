@@ -30,7 +30,7 @@ def test_header_declares_the_expected_entry_points():
     assert names == sorted(
         ["r3d_abi_version", "r3d_last_error", "r3d_sample_mask_words", "r3d_render_fwd", "r3d_render_bwd", "r3d_cast_rays", "r3d_grid_lookup_fwd",
          "r3d_grid_lookup_bwd", "r3d_mark_touched_voxels", "r3d_adam_step", "r3d_multimem_all_reduce", "r3d_sample_statistics",
-         "r3d_density_quad_floats", "r3d_build_density_quads", "r3d_multimem_shard_floats", "r3d_multimem_adam_step", "r3d_has_ab_variants", "r3d_sample_ray_batch"]
+         "r3d_density_quad_floats", "r3d_build_density_quads", "r3d_multimem_shard_floats", "r3d_multimem_adam_step", "r3d_has_ab_variants", "r3d_sample_ray_batch", "r3d_peer_adam_step"]
     )
 
 

@@ -74,7 +74,7 @@ def test_nvls_gradient_all_reduce_matches_nccl(tmp_path):
     assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
 
 
-def _sharded_adam_worker(rank, world, port, tmp):
+def _sharded_adam_worker(rank, world, port, tmp, exchange):
     import torch.distributed as dist
 
     from helpers import CASES, build_inputs, make_cuda_config, make_cuda_grid
@@ -104,7 +104,8 @@ def _sharded_adam_worker(rank, world, port, tmp):
         # fused: reduce-scatter -> shard-local Adam -> all-gather inside the switch
         grid_b = make_cuda_grid(case, inp, dev)
         before = [p.detach().clone() for p in grid_b.parameters()]
-        opt_b = NVLSShardedAdam(grid_b, lr=lr, betas=(0.9, 0.999))
+        opt_b = NVLSShardedAdam(grid_b, lr=lr, betas=(0.9, 0.999), exchange=exchange)
+        assert opt_b.exchange == exchange
         for p, b in zip(grid_b.parameters(), before):
             assert torch.equal(p.detach(), b)  # re-homing keeps the values
         assert opt_b.state["exp_avg"].numel() * world >= opt_b.total  # 1/n of the optimizer state per GPU
@@ -200,9 +201,10 @@ def _sharded_adam_worker(rank, world, port, tmp):
         dist.destroy_process_group()
 
 
-def test_fused_reduce_scatter_adam_all_gather_matches_all_reduce_plus_adam(tmp_path):
-    """reference modules/trainers.py:339-341 (backward -> optimizer.step) across 2 GPUs: the in-switch fused kernel against
-    NCCL all-reduce + torch.optim.Adam, three steps through the real render path."""
+@pytest.mark.parametrize("exchange", ["multimem", "peer"])
+def test_fused_reduce_scatter_adam_all_gather_matches_all_reduce_plus_adam(tmp_path, exchange):
+    """reference modules/trainers.py:339-341 (backward -> optimizer.step) across 2 GPUs: the fused kernel (in-switch multimem
+    version and peer-to-peer version) against NCCL all-reduce + torch.optim.Adam, three steps through the real render path."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import socket
@@ -212,5 +214,5 @@ def test_fused_reduce_scatter_adam_all_gather_matches_all_reduce_plus_adam(tmp_p
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
-    mp.spawn(_sharded_adam_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_sharded_adam_worker, args=(2, port, str(tmp_path), exchange), nprocs=2, join=True)
     assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()

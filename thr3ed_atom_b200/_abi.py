@@ -127,6 +127,10 @@ SIGNATURES = {
         C.c_int,
         [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32] + [C.c_float] * 7 + [C.c_int32, C.c_void_p],
     ),
+    "r3d_peer_adam_step": (
+        C.c_int,
+        [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32] + [C.c_float] * 7 + [C.c_int32, C.c_void_p],
+    ),
     "r3d_adam_step": (
         C.c_int,
         [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64] + [C.c_float] * 7 + [C.c_void_p],

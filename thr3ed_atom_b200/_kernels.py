@@ -391,6 +391,32 @@ def multimem_adam_step(grad_multicast_ptr: int, param_multicast_ptr: int, param_
         )
 
 
+def peer_adam_step(grad_ptrs, param_ptrs, num_floats: int, exp_avg_shard: Tensor, exp_avg_sq_shard: Tensor, rank: int, world_size: int, *,
+                   lr: float, beta1: float, beta2: float, eps: float, step: int, grad_scale: float = 1.0, num_blocks: int = 0) -> None:
+    """Enqueue the fused reduce-scatter -> shard-local Adam -> all-gather kernel over peer-to-peer pointers (``r3d_peer_adam_step``).
+    ``grad_ptrs`` / ``param_ptrs``: one device address per rank (symmetric-memory ``buffer_ptrs``)."""
+    if len(grad_ptrs) != world_size or len(param_ptrs) != world_size:
+        raise ValueError("one gradient and one parameter pointer per rank")
+    for name, t in (("exp_avg_shard", exp_avg_shard), ("exp_avg_sq_shard", exp_avg_sq_shard)):
+        _require_cuda(t, name)
+        if not t.is_contiguous():
+            raise ValueError(f"{name} must be contiguous")
+    shard = multimem_shard_floats(num_floats, world_size)
+    if exp_avg_shard.numel() != shard or exp_avg_sq_shard.numel() != shard:
+        raise ValueError(f"optimizer state shards must hold {shard} floats")
+    device = exp_avg_shard.device
+    g_arr = (C.c_void_p * world_size)(*[int(x) for x in grad_ptrs])
+    p_arr = (C.c_void_p * world_size)(*[int(x) for x in param_ptrs])
+    with torch.cuda.device(device):
+        _abi.check(
+            _abi.lib().r3d_peer_adam_step(
+                g_arr, p_arr, exp_avg_shard.data_ptr(), exp_avg_sq_shard.data_ptr(), num_floats, rank, world_size, lr, beta1, beta2, eps,
+                1.0 - beta1**step, 1.0 - beta2**step, grad_scale, num_blocks, _stream(device),
+            ),
+            "r3d_peer_adam_step",
+        )
+
+
 def has_ab_variants() -> bool:
     """Was the loaded library built with -DR3D_AB_VARIANTS (measurement-only kernel variants selectable)?"""
     return bool(_abi.lib().r3d_has_ab_variants())

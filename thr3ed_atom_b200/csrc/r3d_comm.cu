@@ -123,6 +123,67 @@ __global__ void __launch_bounds__(512) multimem_adam_kernel(const float* __restr
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// The same fused exchange + optimizer over plain peer-to-peer loads / stores (no multicast object needed).  Rank r reads the
+// gradient of its slice from every replica (its own from HBM, the others over NVLink), adds them in rank order, applies
+// Adam with its shard of the state and writes the new parameters into every replica.  Per GPU and direction
+// 2 * (n-1)/n x the slice-sum of bytes cross NVLink: at n = 2 that is 1.0x the gradient bytes, where the in-switch version
+// moves 1.5x (with two ranks the switch pulls the caller's own replica out and back, and multicasts the parameters back to
+// their sender) -- so this is the two-rank path; from n = 4 on the in-switch version moves fewer bytes.
+// ---------------------------------------------------------------------------------------------------------------------
+struct PeerPtrs {
+  const float* grad[8];
+  float* param[8];
+};
+
+template <int UNROLL>
+__global__ void __launch_bounds__(512) peer_adam_kernel(const PeerPtrs pp, int world, int rank, float* __restrict__ m, float* __restrict__ v,
+                                                        long long vec_begin, long long vec_end, float step, float b1, float b2, float eps,
+                                                        float bc2_sqrt, float gscale) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  auto ld_sys = [](const float* p) {  // the peers' gradients were completed before the caller's barrier: system-scope load, never a stale line
+    float4 r;
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p) : "memory");
+    return r;
+  };
+  long long i = vec_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i < vec_end; i += UNROLL * stride) {
+    float4 G[UNROLL], P[UNROLL], M[UNROLL], V[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const long long j = i + u * stride;
+      if (j < vec_end) {
+        G[u] = ld_sys(pp.grad[0] + 4 * j);
+        for (int r = 1; r < world; ++r) {
+          const float4 g = ld_sys(pp.grad[r] + 4 * j);
+          G[u].x += g.x, G[u].y += g.y, G[u].z += g.z, G[u].w += g.w;
+        }
+        P[u] = *reinterpret_cast<const float4*>(pp.param[rank] + 4 * j);
+        M[u] = reinterpret_cast<const float4*>(m)[j - vec_begin];
+        V[u] = reinterpret_cast<const float4*>(v)[j - vec_begin];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const long long j = i + u * stride;
+      if (j < vec_end) {
+#define R3D_ADAM1(c)                                                \
+  {                                                                 \
+    const float gg = G[u].c * gscale;                               \
+    M[u].c = fmaf(b1, M[u].c, (1.0f - b1) * gg);                    \
+    V[u].c = fmaf(b2, V[u].c, (1.0f - b2) * gg * gg);               \
+    P[u].c -= step * (M[u].c / (sqrtf(V[u].c) / bc2_sqrt + eps));   \
+  }
+        R3D_ADAM1(x) R3D_ADAM1(y) R3D_ADAM1(z) R3D_ADAM1(w)
+#undef R3D_ADAM1
+        for (int r = 0; r < world; ++r) *reinterpret_cast<float4*>(pp.param[r] + 4 * j) = P[u];
+        reinterpret_cast<float4*>(m)[j - vec_begin] = M[u];
+        reinterpret_cast<float4*>(v)[j - vec_begin] = V[u];
+      }
+    }
+  }
+}
+
 // slice of rank `rank`, in float4 units: the same partition for the all-reduce and for the fused optimizer
 static void slice_of(long long vecs, int rank, int world, long long& begin, long long& end) {
   const long long per = (vecs + world - 1) / world;
@@ -178,6 +239,37 @@ extern "C" int r3d_multimem_adam_step(void* grad_multicast_ptr, void* param_mult
   else
     multimem_adam_kernel<4><<<blocks, 512, 0, st>>>(gmc, pmc, param_local, exp_avg_shard, exp_avg_sq_shard, begin, end, step, beta1, beta2, eps, bc2s, grad_scale);
   return check_launch("r3d_multimem_adam_step");
+}
+
+extern "C" int r3d_peer_adam_step(const void* const* grad_ptrs, void* const* param_ptrs, float* exp_avg_shard, float* exp_avg_sq_shard,
+                                  int64_t num_floats, int32_t rank, int32_t world_size, float lr, float beta1, float beta2, float eps,
+                                  float bias_correction1, float bias_correction2, float grad_scale, int32_t num_blocks, void* cuda_stream) {
+  if (!grad_ptrs || !param_ptrs || !exp_avg_shard || !exp_avg_sq_shard) return fail(R3D_ERR_INVALID_ARGUMENT, "r3d_peer_adam_step: NULL argument");
+  if (world_size < 1 || world_size > 8 || rank < 0 || rank >= world_size)
+    return fail(R3D_ERR_INVALID_ARGUMENT, "r3d_peer_adam_step: bad rank/world_size (1..8 ranks)");
+  if (num_floats < 0 || (num_floats % 4) != 0 || !aligned16(exp_avg_shard) || !aligned16(exp_avg_sq_shard))
+    return fail(R3D_ERR_INVALID_ARGUMENT, "r3d_peer_adam_step: buffers must be 16-byte aligned and a multiple of 4 floats");
+  PeerPtrs pp{};
+  for (int r = 0; r < world_size; ++r) {
+    if (!grad_ptrs[r] || !param_ptrs[r] || !aligned16(grad_ptrs[r]) || !aligned16(param_ptrs[r]))
+      return fail(R3D_ERR_INVALID_ARGUMENT, "r3d_peer_adam_step: replica %d: NULL or unaligned pointer", r);
+    pp.grad[r] = static_cast<const float*>(grad_ptrs[r]);
+    pp.param[r] = static_cast<float*>(param_ptrs[r]);
+  }
+  if (!(bias_correction1 > 0.f) || !(bias_correction2 > 0.f)) return fail(R3D_ERR_INVALID_ARGUMENT, "r3d_peer_adam_step: bias corrections must be positive");
+  long long begin, end;
+  slice_of(num_floats / 4, rank, world_size, begin, end);
+  if (begin >= end) return R3D_OK;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int blocks = num_blocks > 0 ? num_blocks : sms * 2;
+  const long long need = (end - begin + 511) / 512;
+  if (blocks > need) blocks = (int)need;
+  const float step = lr / bias_correction1, bc2s = sqrtf(bias_correction2);
+  peer_adam_kernel<4><<<blocks, 512, 0, static_cast<cudaStream_t>(cuda_stream)>>>(pp, world_size, rank, exp_avg_shard, exp_avg_sq_shard, begin, end, step,
+                                                                                  beta1, beta2, eps, bc2s, grad_scale);
+  return check_launch("r3d_peer_adam_step");
 }
 
 extern "C" int r3d_multimem_all_reduce(void* multicast_ptr, int64_t num_floats, int32_t rank, int32_t world_size, int32_t num_blocks,

@@ -17,6 +17,8 @@ summed inside the NVSwitch by this repo's own multimem kernel (``csrc/r3d_comm.c
 """
 from __future__ import annotations
 
+import os
+
 import dataclasses
 from typing import Iterable, List, Optional, Tuple
 
@@ -189,10 +191,16 @@ class NVLSShardedAdam:
             opt.step()                                     # barrier -> fused kernel -> barrier, on the current stream
 
     ``param_groups`` is a one-group list with ``lr`` so that ``torch.optim.lr_scheduler``-style code can drive the rate.
-    Raises at construction if symmetric memory / multicast is unavailable.
+    ``exchange``: ``"multimem"`` = the in-switch kernel above; ``"peer"`` = the same fusion over plain peer-to-peer loads /
+    stores of the symmetric buffers (``peer_adam_kernel``; no multicast object needed): rank r reads its slice of every
+    replica's gradient and writes the new parameters into every replica.  With two ranks that moves 1.0x the gradient bytes
+    per NVLink direction where the switch version moves 1.5x, from four ranks on the switch version moves fewer;
+    ``"auto"`` (default, overridable with ``$R3D_SHARDED_ADAM_EXCHANGE``) picks ``"peer"`` for two ranks.
+    Raises at construction if symmetric memory (or, for ``"multimem"``, multicast) is unavailable.
     """
 
-    def __init__(self, module: torch.nn.Module, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, group=None, grad_scale: float = 1.0):
+    def __init__(self, module: torch.nn.Module, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, group=None, grad_scale: float = 1.0,
+                 exchange: str = "auto"):
         import torch.distributed._symmetric_memory as symm_mem
 
         from thr3ed_atom_b200 import _kernels
@@ -216,8 +224,22 @@ class NVLSShardedAdam:
         self._param_handle = symm_mem.rendezvous(self.param_flat, self.group.group_name)
         self.grad_multicast_ptr = int(getattr(self._grad_handle, "multicast_ptr", 0) or 0)
         self.param_multicast_ptr = int(getattr(self._param_handle, "multicast_ptr", 0) or 0)
-        if self.grad_multicast_ptr == 0 or self.param_multicast_ptr == 0:
+        if exchange == "auto":
+            exchange = os.environ.get("R3D_SHARDED_ADAM_EXCHANGE", "auto")
+        if exchange == "auto":
+            exchange = "peer" if self.world_size == 2 else "multimem"
+        if exchange not in ("multimem", "peer"):
+            raise ValueError(f"exchange must be 'auto', 'multimem' or 'peer', got {exchange!r}")
+        self.exchange = exchange
+        if exchange == "multimem" and (self.grad_multicast_ptr == 0 or self.param_multicast_ptr == 0):
             raise RuntimeError("no NVLS multicast mapping for the parameter / gradient buffers on this system")
+        if exchange == "peer":
+            if self.world_size > 8:
+                raise RuntimeError("the peer-to-peer exchange addresses at most 8 replicas")
+            self._grad_peer_ptrs = [int(x) for x in self._grad_handle.buffer_ptrs]
+            self._param_peer_ptrs = [int(x) for x in self._param_handle.buffer_ptrs]
+            if len(self._grad_peer_ptrs) != self.world_size or 0 in self._grad_peer_ptrs or 0 in self._param_peer_ptrs:
+                raise RuntimeError("symmetric memory did not map every peer's buffer into this process")
         self.grad_flat.zero_()
         self.param_flat.zero_()
         self._keys = []
@@ -251,11 +273,14 @@ class NVLSShardedAdam:
         group = self.param_groups[0]
         self.state["step"] += 1
         self._grad_handle.barrier(channel=0)  # every rank has finished accumulating its gradient
-        _kernels.multimem_adam_step(
-            self.grad_multicast_ptr, self.param_multicast_ptr, self.param_flat, self.state["exp_avg"], self.state["exp_avg_sq"],
-            self.rank, self.world_size, lr=float(group["lr"]), beta1=group["betas"][0], beta2=group["betas"][1], eps=group["eps"],
-            step=self.state["step"], grad_scale=self.grad_scale, num_blocks=num_blocks,
-        )
+        hyper = dict(lr=float(group["lr"]), beta1=group["betas"][0], beta2=group["betas"][1], eps=group["eps"], step=self.state["step"],
+                     grad_scale=self.grad_scale, num_blocks=num_blocks)
+        if self.exchange == "peer":
+            _kernels.peer_adam_step(self._grad_peer_ptrs, self._param_peer_ptrs, self.total, self.state["exp_avg"], self.state["exp_avg_sq"],
+                                    self.rank, self.world_size, **hyper)
+        else:
+            _kernels.multimem_adam_step(self.grad_multicast_ptr, self.param_multicast_ptr, self.param_flat, self.state["exp_avg"],
+                                        self.state["exp_avg_sq"], self.rank, self.world_size, **hyper)
         self._param_handle.barrier(channel=1)  # every slice has been updated on every replica
         for p in self.params:
             torch.autograd.graph.increment_version(p)  # written behind autograd's back: derived buffers must notice
