@@ -183,9 +183,10 @@ def run_cuda_case(case: Case, inp: Dict[str, np.ndarray], device, with_grads: bo
     return res
 
 
-def hash_jitter(seed: int, num_rays: int, num_samples: int) -> np.ndarray:
+def hash_jitter(seed: int, num_rays: int, num_samples: int, rays=None) -> np.ndarray:
     """NumPy restatement of the in-kernel counter-based jitter (csrc/r3d_device.cuh: mix32 /
-    ray_rng_key / jitter_u) so that a run with the in-kernel RNG can be replayed through the oracle."""
+    ray_rng_key / jitter_u) so that a run with the in-kernel RNG can be replayed through the oracle.
+    ``rays``: explicit ray indices of the launch (default: all ``num_rays``)."""
     def mix32(h):
         h = h.astype(np.uint32)
         h ^= h >> np.uint32(16)
@@ -197,7 +198,7 @@ def hash_jitter(seed: int, num_rays: int, num_samples: int) -> np.ndarray:
 
     with np.errstate(over="ignore"):
         seed_lo, seed_hi = np.uint32(seed & 0xFFFFFFFF), np.uint32((seed >> 32) & 0xFFFFFFFF)
-        rays = np.arange(num_rays, dtype=np.uint64)
+        rays = np.arange(num_rays, dtype=np.uint64) if rays is None else np.asarray(rays, dtype=np.uint64)
         key = mix32((rays & np.uint64(0xFFFFFFFF)).astype(np.uint32) + seed_lo)
         key = mix32(key ^ seed_hi ^ (rays >> np.uint64(32)).astype(np.uint32))
         samples = (np.arange(num_samples, dtype=np.uint32) * np.uint32(0x9E3779B9)).astype(np.uint32)

@@ -469,6 +469,41 @@ def test_config3_shape_properties(cuda_device):
     assert rel_l2(grid.densities.grad.cpu().numpy(), want["grad_densities"].numpy()) < 1e-4
 
 
+def test_config3_shape_with_in_kernel_jitter_against_the_oracle(cuda_device):
+    """The bench's own path at the bench's own shape (BASELINE configs[2], bench.py: perturb_sampled_points=True with the in-kernel
+    counter-based jitter, image-tile ray order): 256^3 deg-2 grid, 800x800, 256 spp.  2048 strided rays of the full-image launch are
+    replayed through the oracle with the same jitter (tests/helpers.py::hash_jitter, keyed by the ray's index in the launch):
+    forward, and the grid gradient of a loss that only those rays feed."""
+    from oracle import torch_port as tp
+    from cases import relu_field_density_scale
+    from thr3ed_atom_b200.thre3d_reprs.renderers import render_hints, render_sh_voxel_grid
+
+    grid, rays, cfg, dens, feat = _hotdog_setup(256, 2, 800, 256, cuda_device)
+    cfg = dataclasses.replace(cfg, perturb_sampled_points=True)
+    n, S, seed = len(rays), 256, 0x0BADC0FFEE
+    idx = torch.arange(101, n, 307)[:2048]
+    gc_sub = torch.from_numpy(np.random.RandomState(3).normal(size=(idx.numel(), 3)).astype(np.float32)).to(cuda_device)
+    gc = torch.zeros((n, 3), device=cuda_device)
+    gc[idx.to(cuda_device)] = gc_sub
+    with render_hints(image_hw=(800, 800), rng_seed=seed):
+        out = render_sh_voxel_grid(grid, rays, cfg)
+        (out.colour * gc).sum().backward()
+    u = torch.from_numpy(hash_jitter(seed, n, S, rays=idx.numpy())).to(cuda_device)
+    assert 0.45 < float(u.mean()) < 0.55
+    og = tp.OracleGrid(dens.to(cuda_device), feat.to(cuda_device), (3 / 256,) * 3, (0, 0, 0), relu_field_density_scale((3, 3, 3)), "identity", "relu")
+    o, d = rays.origins[idx.to(cuda_device)].contiguous(), rays.directions[idx.to(cuda_device)].contiguous()
+    want = tp.render_with_grads(og, o, d, gc_sub, num_samples=S, near=1.8, far=6.6, white_bkgd=True, jitter=u, ray_chunk=512)
+    sel = idx.to(cuda_device)
+    np.testing.assert_allclose(out.colour[sel].detach().cpu().numpy(), want["colour"].cpu().numpy(), atol=2e-5, rtol=0)
+    np.testing.assert_allclose(out.depth[sel].detach().cpu().numpy(), want["depth"].cpu().numpy(), atol=2e-4, rtol=2e-5)
+    assert rel_l2(grid.feature_storage.grad[..., :27].cpu().numpy(), want["grad_features"].cpu().numpy()) < 1e-4
+    assert rel_l2(grid.densities.grad.cpu().numpy(), want["grad_densities"].cpu().numpy()) < 1e-4
+    # the jitter really moved the samples: the deterministic render of the same rays differs
+    with torch.no_grad(), render_hints(image_hw=(800, 800)):
+        plain = render_sh_voxel_grid(grid, rays, dataclasses.replace(cfg, perturb_sampled_points=False))
+    assert float((plain.colour[sel] - out.colour[sel].detach()).abs().max()) > 1e-3
+
+
 @pytest.mark.parametrize("name", ["deg2_16cube", "deg3_abs", "deg1_aniso_softplus", "c1_32cube_deg0", "deg2_jitter_optimized"])
 def test_cooperative_and_per_ray_kernels_agree(name, cuda_device, monkeypatch):
     """The warp-cooperative kernels against the thread-per-ray kernels (variant 3), with and without the forward's sample
