@@ -58,6 +58,10 @@
 #ifndef R3D_FWD_PIPE
 #define R3D_FWD_PIPE 0  // measured at c3: 5.44 ms pipelined vs 4.41 ms (4 CTAs/SM), 5.40 vs 5.29 ms (3 CTAs/SM)
 #endif
+// forward lane-group kernel: packed FFMA2 in the record accumulation (bit-identical; measured at c3: 4.43 -> 4.37 ms)
+#ifndef R3D_FWD_FFMA2
+#define R3D_FWD_FFMA2 1
+#endif
 #ifndef R3D_BWD_BLOCKS
 #define R3D_BWD_BLOCKS 5
 #endif
@@ -1046,11 +1050,23 @@ __device__ __forceinline__ void fwd_group_body(const GridP& g, const RaysP& rp, 
           const float4 w1 = *reinterpret_cast<const float4*>(sm.W + m * 8 + 4);
           const float4 y4 = *reinterpret_cast<const float4*>(sm.Y + sm.src[m] * H::YROW + 4 * cj);
           const float wk[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#if R3D_FWD_FFMA2
+          {  // packed fp32 FMA: two record elements per issue slot (same products, same order per element)
+            float2 a01 = make_float2(0.f, 0.f), a23 = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              a01 = ffma2(make_float2(q[k].x, q[k].y), wk[k], a01);
+              a23 = ffma2(make_float2(q[k].z, q[k].w), wk[k], a23);
+            }
+            a = make_float4(a01.x, a01.y, a23.x, a23.y);
+          }
+#else
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             a.x = fmaf(wk[k], q[k].x, a.x), a.y = fmaf(wk[k], q[k].y, a.y);
             a.z = fmaf(wk[k], q[k].z, a.z), a.w = fmaf(wk[k], q[k].w, a.w);
           }
+#endif
           if constexpr (DUAL && DEG > 0) {  // band-0 radiance: C0 * interpolated coeff[ch][0] (Y[0] = C0 for every ray)
             if (dslot >= 0) sm.R2[m * 4 + dslot] = 0.28209479177387814f * (dcomp == 0 ? a.x : (dcomp == 1 ? a.y : (dcomp == 2 ? a.z : a.w)));
           }
