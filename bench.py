@@ -216,7 +216,29 @@ def run_reference_arm(args):
         "e2e": {"value": rps, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT_FD = None
+
+
+def reserve_stdout_for_the_json_line() -> None:
+    """stdout carries exactly ONE line, the result.  Libraries write there too (NCCL prints its version banner to stdout at any
+    NCCL_DEBUG level): point file descriptor 1 at stderr for the whole run and keep the real stdout for `emit`."""
+    global _REAL_STDOUT_FD
+    if _REAL_STDOUT_FD is None:
+        sys.stdout.flush()
+        _REAL_STDOUT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT_FD is None:
+        sys.stdout.write(data.decode()), sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT_FD, data)
 
 
 def fp32_peak_tflops(sm_mhz: float, sms: int = 148) -> float:
@@ -311,6 +333,7 @@ def pytorch_gpu_baseline(workload: str, device, chunk: int = 32768, chunks: int 
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 def main():
+    reserve_stdout_for_the_json_line()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -360,8 +383,6 @@ def main():
     device = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL writes its debug output -- at any NCCL_DEBUG level its version banner -- to stdout; stdout carries the one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
     assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
@@ -734,7 +755,7 @@ def main():
                 line["cpu_baseline"] = {"value": rps, "unit": "rays/s", "cores": threads, "kind": "port",
                                         "sample": f"{sample} strided rays of the same {side}x{side} view, fwd+bwd, {mean_s:.2f} s per pass, extrapolated "
                                                   f"to the {n_rays}-ray batch, + one dense torch.optim.Adam step over the grid ({adam_s:.2f} s)"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
