@@ -662,9 +662,12 @@ def main():
             ready.record(copy_stream)
         return staged, ready
 
+    trace = os.environ.get("R3D_BENCH_E2E_TRACE") == "1"  # host-side timeline of the e2e loop on stderr (diagnostic)
+
     def e2e_steps(count):
         nxt = stage_inputs()
         for k in range(count):
+            t_a = time.perf_counter()
             (o, d, px), ready = nxt
             main = torch.cuda.current_stream(device)
             main.wait_event(ready)
@@ -672,16 +675,27 @@ def main():
                 t.record_stream(main)
             if k + 1 < count:
                 nxt = stage_inputs()  # next step's inputs fly while this step computes
+            t_b = time.perf_counter()
             step(o, d, px, after_loss=read_back)
+            t_c = time.perf_counter()
             read_done.synchronize()
             float(loss_host.item())
+            if trace and rank == 0:
+                t_d = time.perf_counter()
+                print(f"[e2e trace] step {k}: stage {1e3 * (t_b - t_a):.3f} ms, queue step {1e3 * (t_c - t_b):.3f} ms, wait read-back {1e3 * (t_d - t_c):.3f} ms",
+                      file=sys.stderr)
 
     e2e_steps(1)
     barrier()
+    import gc
+
+    gc.collect()
+    gc.disable()  # the e2e figure is wall clock: keep a collector pause out of it
     t0 = time.perf_counter()
     e2e_steps(args.steps)
     barrier()
     e2e_s = time.perf_counter() - t0
+    gc.enable()
 
     # ---- max over ranks ----
     t = torch.tensor([total_ms, e2e_s * 1e3, fwd_ms, bwd_ms, opt_ms], dtype=torch.float64, device=device)

@@ -343,10 +343,21 @@ def test_fused_adam_matches_torch_adam(cuda_device):
     m, v = torch.zeros_like(p), torch.zeros_like(p)
     for step in range(1, 6):
         g = torch.randn(n, generator=gen).to(cuda_device) * (step % 3)
+        # the kernel keeps the stores of 16-byte groups whose gradient and moments are all zero (identity update): elements
+        # 400..799 never receive a gradient, 800..1199 only from step 3 on, 1200..1599 only at step 1 (their moments then decay),
+        # and 1601..1602 sit in groups whose other elements are live
+        g[400:800] = 0.0
+        if step < 3:
+            g[800:1200] = 0.0
+        if step > 1:
+            g[1200:1600] = 0.0
+        g[1601:1603] = 0.0
         p_ref.grad = g.clone()
         opt.step()
         _kernels.adam_step(p, g, m, v, lr=0.03, beta1=0.9, beta2=0.999, eps=1e-8, step=step)
         np.testing.assert_allclose(p.cpu().numpy(), p_ref.detach().cpu().numpy(), rtol=2e-6, atol=1e-6)
+    assert torch.equal(p[400:800].cpu(), p0[400:800]) and not bool(m[400:800].any()) and not bool(v[400:800].any())
+    assert bool((m[1200:1600] != 0).all())  # decaying moments keep being written
 
 
 # ---------------------------------------------------------------------------------------------

@@ -92,7 +92,9 @@ __global__ void __launch_bounds__(256) lookup_bwd_kernel(const GridP g, const fl
 
 // Adam, torch.optim.Adam semantics (no weight decay / amsgrad / maximize):
 //   m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
-// Pure streaming kernel: 4 reads + 3 writes of 4 B per element.
+// Pure streaming kernel: 4 reads + 3 writes of 4 B per element.  A 16-byte group whose gradient AND moments are all zero (voxels no
+// ray has reached since training began: g = 0, m = v = 0  =>  m' = v' = 0 and p' = p - step * 0 / eps = p exactly) keeps its three
+// stores: the update is the identity there, 12 of its 28 bytes of traffic are not spent.
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ gr, float* __restrict__ m,
                                                    float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
                                                    float bc1, float bc2_sqrt, float gscale) {
@@ -110,6 +112,9 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
     V.c = fmaf(b2, V.c, (1.0f - b2) * gg * gg);              \
     P.c -= step * (M.c / (sqrtf(V.c) / bc2_sqrt + eps));     \
   }
+    const bool still = G.x == 0.0f && G.y == 0.0f && G.z == 0.0f && G.w == 0.0f && M.x == 0.0f && M.y == 0.0f && M.z == 0.0f && M.w == 0.0f &&
+                       V.x == 0.0f && V.y == 0.0f && V.z == 0.0f && V.w == 0.0f;
+    if (still) continue;
     R3D_ADAM1(x) R3D_ADAM1(y) R3D_ADAM1(z) R3D_ADAM1(w)
     reinterpret_cast<float4*>(p)[i] = P;
     reinterpret_cast<float4*>(m)[i] = M;

@@ -64,6 +64,13 @@ __global__ void __launch_bounds__(512) multimem_allreduce_kernel(float* __restri
 // 7-streams-per-element optimizer pass over the whole grid disappears from every GPU, and so do 7/8 of its state.
 // The caller brackets the launch with cross-rank barriers (all gradients complete before; all parameters updated after).
 // ---------------------------------------------------------------------------------------------------------------------
+// summed gradient and both moments of a 16-byte group all zero (voxels no ray of any rank has reached since training began): the Adam
+// update is the identity (m' = v' = 0, p' = p - step * 0 / eps = p), so the group needs no store and no broadcast
+__device__ __forceinline__ bool still(const float4& G, const float4& M, const float4& V) {
+  return G.x == 0.0f && G.y == 0.0f && G.z == 0.0f && G.w == 0.0f && M.x == 0.0f && M.y == 0.0f && M.z == 0.0f && M.w == 0.0f && V.x == 0.0f &&
+         V.y == 0.0f && V.z == 0.0f && V.w == 0.0f;
+}
+
 template <int UNROLL>
 __global__ void __launch_bounds__(512) multimem_adam_kernel(const float* __restrict__ grad_mc, float* __restrict__ param_mc,
                                                             const float* __restrict__ param_local, float* __restrict__ m, float* __restrict__ v,
@@ -98,6 +105,7 @@ __global__ void __launch_bounds__(512) multimem_adam_kernel(const float* __restr
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
       const long long j = i + u * stride;
+      if (still(G[u], M[u], V[u])) continue;  // identity update: nothing to store, nothing to broadcast
       update(G[u], P[u], M[u], V[u]);
       asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(param_mc + 4 * j), "f"(P[u].x), "f"(P[u].y),
                    "f"(P[u].z), "f"(P[u].w)
@@ -115,6 +123,7 @@ __global__ void __launch_bounds__(512) multimem_adam_kernel(const float* __restr
     P = *reinterpret_cast<const float4*>(param_local + 4 * i);
     M = reinterpret_cast<const float4*>(m)[i - vec_begin];
     V = reinterpret_cast<const float4*>(v)[i - vec_begin];
+    if (still(G, M, V)) continue;
     update(G, P, M, V);
     asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(param_mc + 4 * i), "f"(P.x), "f"(P.y), "f"(P.z), "f"(P.w)
                  : "memory");
@@ -166,7 +175,7 @@ __global__ void __launch_bounds__(512) peer_adam_kernel(const PeerPtrs pp, int w
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
       const long long j = i + u * stride;
-      if (j < vec_end) {
+      if (j < vec_end && !still(G[u], M[u], V[u])) {
 #define R3D_ADAM1(c)                                                \
   {                                                                 \
     const float gg = G[u].c * gscale;                               \
