@@ -409,6 +409,22 @@ def test_bench_reports_the_dominant_kernel_in_the_roofline_entry():
         assert key in r["roofline"]
 
 
+def test_bench_stdout_carries_only_the_json_line():
+    """bench.py reserves file descriptor 1 for its one JSON line: whatever a library prints to stdout during the run (NCCL's
+    version banner did) lands on stderr."""
+    import json
+    import subprocess
+    import sys
+
+    code = ("import bench, os; bench.reserve_stdout_for_the_json_line(); print('python-level noise'); "
+            "os.system('echo child-process noise'); bench.emit({'metric': 'x', 'value': 1.5})")
+    repo = str(__import__("pathlib").Path(__file__).resolve().parent.parent)
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=repo, timeout=300)
+    assert p.returncode == 0, p.stderr
+    assert json.loads(p.stdout) == {"metric": "x", "value": 1.5} and p.stdout.count("\n") == 1
+    assert "python-level noise" in p.stderr and "child-process noise" in p.stderr
+
+
 def test_bench_refuses_stale_dram_traffic_numbers(tmp_path, monkeypatch):
     """profiles/traffic.json is stamped with the digest of the library sources it was measured with; any other digest => null."""
     import importlib.util
