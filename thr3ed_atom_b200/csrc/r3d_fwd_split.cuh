@@ -346,10 +346,15 @@ __global__ void __launch_bounds__(128, DEG >= 3 ? 4 : R3D_SPLIT_GATHER_BLOCKS)
         const float y0 = ypad[0] ? 0.0f : Yr[yk[0]], y1 = ypad[1] ? 0.0f : Yr[yk[1]];
         const float y2 = ypad[2] ? 0.0f : Yr[yk[2]], y3 = ypad[3] ? 0.0f : Yr[yk[3]];
         const float wk[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-        if constexpr (PFK == 9) {  // measurement only: the gather without its arithmetic (one add per record keeps the loads alive)
+        if constexpr (PFK == 9) {  // measurement only: the gather without its arithmetic.  All four components of every load are
+          // consumed (ptxas narrows a vector load whose upper components are dead): two LOP3 per record instead of two FFMA2
+          unsigned bits = 0u;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) a.x += q[e].x * wk[e];
-          a.x *= y0 + y1 + y2 + y3;
+          for (int e = 0; e < 8; ++e) {
+            bits ^= __float_as_uint(q[e].x) ^ __float_as_uint(q[e].y);
+            bits ^= __float_as_uint(q[e].z) ^ __float_as_uint(q[e].w);
+          }
+          a.x = __uint_as_float((bits & 0x007fffffu) | 0x3f000000u) * (wk[0] + wk[7]) * (y0 + y1 + y2 + y3);
         } else {
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
