@@ -102,6 +102,21 @@ def test_argument_validation_reports_through_last_error(lib):
     with pytest.raises(RuntimeError, match="num_samples_per_ray"):
         _abi.check(1, "r3d_render_fwd")
     assert lib.r3d_adam_step(None, None, None, None, 8, 0.1, 0.9, 0.999, 1e-8, 0.1, 0.001, 1.0, None) == 1
+    # fused exchange + optimizer entry points: every argument error is caught before a kernel is enqueued
+    hyper = (0.1, 0.9, 0.999, 1e-8, 0.1, 0.001, 1.0)
+    assert lib.r3d_multimem_adam_step(None, None, None, None, None, 8, 0, 2, *hyper, 0, None) == 1
+    assert b"multicast pointer is NULL" in lib.r3d_last_error()
+    assert lib.r3d_peer_adam_step(None, None, None, None, 8, 0, 2, *hyper, 0, None) == 1
+    assert b"NULL argument" in lib.r3d_last_error()
+    two = (C.c_void_p * 2)(32, 0)  # replica 1 missing
+    assert lib.r3d_peer_adam_step(two, two, 32, 32, 8, 0, 2, *hyper, 0, None) == 1
+    assert b"replica 1" in lib.r3d_last_error()
+    ok2 = (C.c_void_p * 2)(32, 64)
+    assert lib.r3d_peer_adam_step(ok2, ok2, 32, 32, 8, 2, 2, *hyper, 0, None) == 1  # rank out of range
+    assert lib.r3d_peer_adam_step(ok2, ok2, 32, 32, 8, 0, 9, *hyper, 0, None) == 1  # more replicas than the kernel addresses
+    assert b"1..8 ranks" in lib.r3d_last_error()
+    assert lib.r3d_peer_adam_step(ok2, ok2, 32, 32, 6, 0, 2, *hyper, 0, None) == 1  # not a multiple of 4 floats
+    assert lib.r3d_multimem_shard_floats(16, 3) == 8 and lib.r3d_multimem_shard_floats(6, 2) == -1
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
