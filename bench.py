@@ -292,6 +292,35 @@ def load_traffic(workload: str) -> dict:
         return {"source": f"unavailable ({e.__class__.__name__})"}
 
 
+def sm_side_ceiling(workload: str, fwd_ms: float) -> dict:
+    """Companion of `roofline_fwd`: the forward is bound inside the SM, not by HBM, so next to the HBM fraction the line
+    carries the time of a forward that moves the same data and computes nothing -- the two-kernel forward of the measurement build
+    (probe kernel + gather kernel, csrc/r3d_fwd_split.cuh) with the gather's arithmetic removed (full-width loads kept alive by two LOP3
+    per record), measured HERE in a subprocess on the same GPU after the timed region.  Needs the measurement build
+    (`python -m thr3ed_atom_b200.build --ab`) made from the current sources; otherwise the entry says why it is absent."""
+    import subprocess
+
+    from thr3ed_atom_b200 import build as _build
+
+    if workload != "c3_256cube_deg2_800px_256spp":
+        return {"unavailable": "measured for the c3 workload only"}
+    if not _build.ab_is_current():
+        return {"unavailable": "no measurement build of the current sources (python -m thr3ed_atom_b200.build --ab)"}
+    env = dict(os.environ, R3D_LIB_PATH=str(_build.AB_LIB_PATH), R3D_SPLIT_MODE="9")
+    proc = subprocess.run([sys.executable, str(ROOT / "profiles" / "ab_kernels.py"), "--variants", "32768", "--iters", "5", "--warmup", "2"],
+                          env=env, capture_output=True, text=True, timeout=300, stdin=subprocess.DEVNULL)
+    if proc.returncode != 0:
+        return {"unavailable": f"measurement run failed: {proc.stderr[-200:]}"}
+    res = json.loads(proc.stdout)["results"][0]
+    floor_ms = float(res["fwd_ms"])
+    return {
+        "no_arithmetic_two_kernel_forward_ms": floor_ms, "forward_ms": fwd_ms, "forward_over_floor": fwd_ms / floor_ms,
+        "what": "probe kernel (march, density, depth / acc) + gather kernel with its arithmetic removed (same addresses, same shared-memory "
+                "hand-over, full-width loads), run back to back on this GPU; the fused product forward overlaps the two phases and does the "
+                "arithmetic. The gather is bound by the L1 data pipe (profiles/r02_split_forward_ncu.md: 86 % busy), not by HBM.",
+    }
+
+
 def pytorch_gpu_baseline(workload: str, device, chunk: int = 32768, chunks: int = 4):
     """Informational row: the reference's op-by-op PyTorch path (the oracle port: same ATen ops in the
     same order) on the SAME B200, forward + backward, ray-chunked at 32768 as the reference itself has to be
@@ -772,6 +801,12 @@ def main():
                 except Exception as e:  # noqa: BLE001  (informational row: never fail the bench line)
                     line["pytorch_gpu_baseline"] = {"unavailable": repr(e)[:200]}
                 torch.cuda.empty_cache()
+                try:
+                    line["roofline_fwd"]["sm_side_ceiling"] = sm_side_ceiling(args.workload, fwd_ms)
+                except Exception as e:  # noqa: BLE001  (companion figure: never fail the bench line)
+                    line["roofline_fwd"]["sm_side_ceiling"] = {"unavailable": repr(e)[:200]}
+                if line["roofline"].get("kernel") == "render_fwd_group_kernel":
+                    line["roofline"]["sm_side_ceiling"] = line["roofline_fwd"]["sm_side_ceiling"]
             if not args.no_cpu_baseline:
                 threads = os.cpu_count() or 1
                 rps, mean_s, sample, adam_s = cpu_oracle_rays_per_sec(args.workload, args.cpu_sample_rays, steps=2, warmup=1, threads=threads,

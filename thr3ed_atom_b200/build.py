@@ -56,6 +56,7 @@ def is_current() -> bool:
 
 
 AB_LIB_PATH = LIB_DIR / "libr3d_b200_ab.so"
+AB_STAMP = LIB_DIR / "libr3d_b200_ab.stamp"
 
 
 def build_ab(verbose: bool = False) -> Path:
@@ -71,7 +72,13 @@ def build_ab(verbose: bool = False) -> Path:
         raise RuntimeError(f"nvcc failed ({proc.returncode}):\n{' '.join(cmd)}\n{proc.stdout}\n{proc.stderr}")
     if verbose:
         sys.stderr.write(proc.stderr)
+    AB_STAMP.write_text(_source_digest())
     return AB_LIB_PATH
+
+
+def ab_is_current() -> bool:
+    """Was the measurement build made from the current sources?"""
+    return AB_LIB_PATH.exists() and AB_STAMP.exists() and AB_STAMP.read_text().strip() == _source_digest()
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
