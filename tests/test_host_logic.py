@@ -425,6 +425,18 @@ def test_bench_stdout_carries_only_the_json_line():
     assert "python-level noise" in p.stderr and "child-process noise" in p.stderr
 
 
+def test_bench_sm_side_ceiling_is_absent_with_a_reason_not_with_an_error(monkeypatch):
+    """The self-measured companion of roofline_fwd needs the measurement build of the CURRENT sources; without it (or for another
+    workload) the bench line carries the reason, never a stale number and never an exception."""
+    import bench
+    from thr3ed_atom_b200 import build as _build
+
+    assert "c3 workload only" in bench.sm_side_ceiling("c2_128cube_deg2_400px_128spp", 1.0)["unavailable"]
+    monkeypatch.setattr(_build, "ab_is_current", lambda: False)
+    out = bench.sm_side_ceiling("c3_256cube_deg2_800px_256spp", 4.4)
+    assert "build --ab" in out["unavailable"] and "no_arithmetic_two_kernel_forward_ms" not in out
+
+
 def test_bench_refuses_stale_dram_traffic_numbers(tmp_path, monkeypatch):
     """profiles/traffic.json is stamped with the digest of the library sources it was measured with; any other digest => null."""
     import importlib.util
